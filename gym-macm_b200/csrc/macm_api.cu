@@ -1,0 +1,376 @@
+// macm_api.cu -- the C ABI of libmacm.so (include/macm.h): parameter validation, derivation of the
+// fp32 engine constants exactly as pybox2d's SWIG boundary would round them, buffer binding,
+// kernel launches, and the host-buffer convenience path.  No CPU fallback exists: without a CUDA
+// device every entry point that needs one returns MACM_E_CUDA.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+
+#include "macm_sim.h"
+
+struct macm_sim {
+    macm_params params;
+    SimConst K;
+    LaunchCfg cfg;
+    int device;
+    int bound;
+    int blocks_per_sm, sm_count;
+    int64_t launches;
+    char cuda_err[256];
+    // host-buffer path
+    cudaStream_t hstream;
+    void* d_actions;
+    size_t d_actions_bytes;
+};
+
+static int fail_cuda(macm_sim* s, cudaError_t e, const char* where)
+{
+    if (s) snprintf(s->cuda_err, sizeof(s->cuda_err), "%s: %s", where, cudaGetErrorString(e));
+    return MACM_E_CUDA;
+}
+#define CU(call)                                                   \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return fail_cuda(sim, e_, #call);   \
+    } while (0)
+
+extern "C" int macm_abi_version(void) { return MACM_ABI_VERSION; }
+
+extern "C" const char* macm_strerror(int status)
+{
+    switch (status) {
+        case MACM_OK: return "ok";
+        case MACM_E_INVALID: return "invalid argument";
+        case MACM_E_CUDA: return "CUDA error (see macm_last_cuda_error)";
+        case MACM_E_UNBOUND: return "buffers not bound";
+        case MACM_E_ALIGN: return "buffer misaligned";
+        case MACM_E_NOMEM: return "out of memory";
+        case MACM_E_UNSUPPORTED: return "unsupported";
+        default: return "unknown status";
+    }
+}
+
+extern "C" const char* macm_last_cuda_error(const macm_sim* sim) { return sim ? sim->cuda_err : ""; }
+
+extern "C" int macm_params_default(macm_params* p, int env_kind)
+{
+    if (!p || (env_kind != MACM_ENV_FLOCK && env_kind != MACM_ENV_TDM)) return MACM_E_INVALID;
+    memset(p, 0, sizeof(*p));
+    p->env_kind = env_kind;
+    p->n_envs = 1;
+    p->n_agents = env_kind == MACM_ENV_FLOCK ? 10 : 2;   // mvmnt.py:35, combat.py:61
+    p->n_targets = env_kind == MACM_ENV_FLOCK ? 1 : 0;
+    p->hz = 60.0;
+    p->velocity_iterations = 8;
+    p->position_iterations = 3;
+    p->warm_starting = 1;
+    p->damping_model = MACM_DAMPING_TAYLOR;
+    p->radius = 0.5;
+    p->density = 1.0;
+    p->friction = 0.3;
+    p->linear_damping = 5.0;
+    p->agent_force = 20.0;
+    p->agent_rotation_speed = 0.8 * (2 * NP_PI);
+    p->time_limit = 60.0;
+    p->reward_mode = MACM_REWARD_BINARY;
+    p->action_mode = MACM_ACTION_DISCRETE;
+    p->coord = MACM_COORD_POLAR;
+    p->flags = MACM_FLAG_REPAIR_MOV_COOLDOWN;
+    p->reward_radius = 7.0;
+    p->cooldown_atk = 1.0;
+    p->cooldown_mov_penalty = 0.5;
+    p->melee_range = 2.0;
+    p->melee_dmg = 0.25;
+    p->percent_mov_penalty = 0.2;
+    p->init_health = 1.0;
+    p->start_spread = 20.0;
+    p->start_x = 0.0;
+    p->start_y = 0.0;
+    p->target_mindist = 25.0;
+    p->target_maxdist = 60.0;
+    p->world_width = 30.0;
+    p->world_height = 30.0;
+    return MACM_OK;
+}
+
+// number of `c -= 1/hz` float64 decrements until c <= 0 (combat.py:142,155)
+static int cooldown_steps(double c, double hz)
+{
+    int k = 0;
+    while (c > 0 && k < (1 << 24)) { c -= (1 / hz); ++k; }
+    return k;
+}
+
+static int derive_constants(macm_sim* sim)
+{
+    const macm_params& p = sim->params;
+    SimConst& K = sim->K;
+    memset(&K, 0, sizeof(K));
+    K.E = p.n_envs; K.N = p.n_agents; K.T = p.n_targets;
+    const int pairs = p.n_agents * (p.n_agents - 1) / 2;
+    int C = p.max_contacts > 0 ? p.max_contacts : (pairs < 8 * p.n_agents ? pairs : 8 * p.n_agents);
+    if (C > pairs) C = pairs;
+    if (C < 1) C = 1;
+    int TC = p.max_touching > 0 ? p.max_touching : (C < 2 * p.n_agents ? C : 2 * p.n_agents);
+    if (TC > C) TC = C;
+    TC = (TC + 15) / 16 * 16;
+    if (TC > 240) TC = 240;  // levels are bytes; the DFS keeps one taken-bit per chunk of G contacts
+    K.C = C; K.TC = TC;
+    K.kind = p.env_kind; K.reward_mode = p.reward_mode; K.action_mode = p.action_mode; K.coord = p.coord;
+    K.vel_iters = p.velocity_iterations; K.pos_iters = p.position_iterations;
+    K.warm_starting = p.warm_starting; K.flags = p.flags;
+    K.obs_dim = p.env_kind == MACM_ENV_TDM ? 4 * p.n_agents : (p.coord == MACM_COORD_POLAR ? 4 : 6);
+
+    // cm_framework.py:182,222: timeStep = 1.0/hz is a Python float, rounded to float32 by SWIG
+    K.h = (float)(1.0 / p.hz);
+    const float inv_dt = 1.0f / K.h;          // b2World::Step: step.inv_dt
+    K.dt_ratio = inv_dt * K.h;                // m_inv_dt0 * dt from the second step on
+    K.radius = (float)p.radius;
+    const float mass = (float)p.density * B2_PI * K.radius * K.radius;  // b2CircleShape::ComputeMass
+    K.inv_mass = 1.0f / mass;
+    const float fr = (float)p.friction;
+    K.friction = sqrtf(fr * fr);              // b2MixFriction
+    const float ld = (float)p.linear_damping;
+    if (p.damping_model == MACM_DAMPING_TAYLOR) {
+        float d = 1.0f - K.h * ld;
+        K.damp = d < 0.0f ? 0.0f : (d > 1.0f ? 1.0f : d);
+    } else {
+        K.damp = 1.0f / (1.0f + K.h * ld);
+    }
+    const float rsum = K.radius + K.radius;
+    K.rsum2 = rsum * rsum;
+    K.k_sum = K.inv_mass + K.inv_mass;
+    K.normal_mass = K.k_sum > 0.0f ? 1.0f / K.k_sum : 0.0f;
+
+    // binary reward: int(sqrt64(d2_f32) < reward_radius)  <=>  d2_f32 < thr  (sqrt is monotone)
+    {
+        const double R = p.reward_radius;
+        float x = (float)(R * R);
+        if (!(R > 0)) x = 0.0f;
+        else {
+            while (sqrt((double)x) < R) x = nextafterf(x, INFINITY);
+            while (x > 0.0f && !(sqrt((double)nextafterf(x, -INFINITY)) < R)) x = nextafterf(x, -INFINITY);
+        }
+        K.binary_thr = x;
+    }
+    // done = (time_passed > time_limit) with time_passed accumulated in float64 (mvmnt.py:134-136)
+    {
+        double t = 0.0;
+        int k = 0;
+        const int cap = 1 << 28;
+        while (k < cap) { t += (1 / p.hz); ++k; if (t > p.time_limit) break; }
+        K.done_step = k < cap ? k : 0x7fffffff;
+    }
+    K.rot_step = p.agent_rotation_speed * (1 / p.hz);
+    K.force = p.agent_force;
+    K.force_pen = p.agent_force * (1 - p.percent_mov_penalty * 1);
+    K.diag = 1 / sqrt(2.0);
+    K.melee_range = p.melee_range;
+    K.melee_dmg = (float)p.melee_dmg;
+    K.init_health = (float)p.init_health;
+    K.cd_atk_steps = cooldown_steps(p.cooldown_atk, p.hz);
+    K.cd_mov_steps = cooldown_steps(p.cooldown_mov_penalty, p.hz);
+    return MACM_OK;
+}
+
+extern "C" int macm_create(macm_sim** out, const macm_params* p, int device)
+{
+    if (!out || !p) return MACM_E_INVALID;
+    *out = nullptr;
+    if (p->env_kind != MACM_ENV_FLOCK && p->env_kind != MACM_ENV_TDM) return MACM_E_INVALID;
+    if (p->n_envs < 1 || p->n_agents < 2 || p->n_agents > MACM_MAX_AGENTS) return MACM_E_INVALID;
+    if (p->env_kind == MACM_ENV_FLOCK && (p->n_targets < 1 || p->n_targets > MACM_MAX_TARGETS)) return MACM_E_INVALID;
+    if (!(p->hz > 0) || !(p->radius > 0) || !(p->density > 0) || p->friction < 0 || p->linear_damping < 0)
+        return MACM_E_INVALID;
+    if (p->velocity_iterations < 0 || p->position_iterations < 0) return MACM_E_INVALID;
+    if (p->reward_mode < 0 || p->reward_mode > 1 || p->action_mode < 0 || p->action_mode > 1 || p->coord < 0 ||
+        p->coord > 1 || p->damping_model < 0 || p->damping_model > 1)
+        return MACM_E_INVALID;
+    if (p->env_kind == MACM_ENV_TDM) return MACM_E_UNSUPPORTED;  // TODO(round 1): TDM kernel
+
+    macm_sim* sim = new (std::nothrow) macm_sim;
+    if (!sim) return MACM_E_NOMEM;
+    memset(sim, 0, sizeof(*sim));
+    sim->params = *p;
+    sim->device = device;
+    int rc = derive_constants(sim);
+    if (rc != MACM_OK) { delete sim; return rc; }
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        // report through a static string: the handle is not returned
+        delete sim;
+        return MACM_E_CUDA;
+    }
+    *out = sim;
+    CU(cudaSetDevice(device));
+    CU(cudaDeviceGetAttribute(&sim->sm_count, cudaDevAttrMultiProcessorCount, device));
+    e = macm_launch_cfg(sim->K, &sim->cfg);
+    if (e != cudaSuccess) { *out = nullptr; delete sim; return MACM_E_INVALID; }
+    CU(macm_prepare_kernels(sim->K, sim->cfg, &sim->blocks_per_sm));
+    return MACM_OK;
+}
+
+extern "C" int macm_destroy(macm_sim* sim)
+{
+    if (!sim) return MACM_E_INVALID;
+    cudaSetDevice(sim->device);
+    if (sim->d_actions) cudaFree(sim->d_actions);
+    if (sim->hstream) cudaStreamDestroy(sim->hstream);
+    delete sim;
+    return MACM_OK;
+}
+
+extern "C" int macm_get_buffer_sizes(const macm_sim* sim, macm_buffer_sizes* o)
+{
+    if (!sim || !o) return MACM_E_INVALID;
+    memset(o, 0, sizeof(*o));
+    const SimConst& K = sim->K;
+    const uint64_t EN = (uint64_t)K.E * K.N;
+    o->posvel = EN * 16; o->angsleep = EN * 8; o->fat = EN * 16;
+    o->contact_ab = (uint64_t)K.E * K.C * 4; o->contact_imp = (uint64_t)K.E * K.C * 8;
+    o->contact_count = (uint64_t)K.E * 4; o->env_state = (uint64_t)K.E * 16;
+    o->targets = (uint64_t)K.E * K.T * 8; o->target_idx = K.kind == MACM_ENV_FLOCK ? (uint64_t)K.N : 0;
+    o->tdm_state = K.kind == MACM_ENV_TDM ? EN * 16 : 0; o->team = K.kind == MACM_ENV_TDM ? (uint64_t)K.N : 0;
+    o->obs = EN * 4 * (uint64_t)K.obs_dim; o->nn_idx = K.kind == MACM_ENV_FLOCK ? EN * 4 : 0;
+    o->rewards = EN * 4; o->collided = EN; o->done = (uint64_t)K.E;
+    o->obs_dim = K.obs_dim;
+    o->action_bytes = sim->params.action_mode == MACM_ACTION_DISCRETE ? 4 : 8;
+    o->max_contacts = K.C; o->max_touching = K.TC;
+    return MACM_OK;
+}
+
+extern "C" int macm_get_launch_info(const macm_sim* sim, macm_launch_info* o)
+{
+    if (!sim || !o) return MACM_E_INVALID;
+    o->lanes_per_env = sim->cfg.G; o->agents_per_lane = sim->cfg.APL; o->envs_per_block = sim->cfg.envs_per_block;
+    o->threads_per_block = sim->cfg.threads; o->blocks = sim->cfg.blocks; o->smem_bytes_per_block = sim->cfg.smem_bytes;
+    o->blocks_per_sm = sim->blocks_per_sm; o->sm_count = sim->sm_count; o->done_step = sim->K.done_step;
+    o->dt = sim->K.h; o->dt_ratio = sim->K.dt_ratio; o->inv_mass = sim->K.inv_mass; o->damping_factor = sim->K.damp;
+    o->binary_d2_threshold = sim->K.binary_thr;
+    return MACM_OK;
+}
+
+static bool aligned(const void* p, size_t a) { return ((uintptr_t)p % a) == 0; }
+
+extern "C" int macm_bind(macm_sim* sim, const macm_buffers* b)
+{
+    if (!sim || !b) return MACM_E_INVALID;
+    SimConst& K = sim->K;
+    const bool flock = K.kind == MACM_ENV_FLOCK;
+    if (!b->posvel || !b->angsleep || !b->fat || !b->contact_ab || !b->contact_imp || !b->contact_count ||
+        !b->env_state || !b->obs || !b->rewards || !b->collided || !b->done)
+        return MACM_E_UNBOUND;
+    if (flock && (!b->targets || !b->target_idx || !b->nn_idx)) return MACM_E_UNBOUND;
+    if (!flock && (!b->tdm_state || !b->team)) return MACM_E_UNBOUND;
+    if (!aligned(b->posvel, 16) || !aligned(b->fat, 16) || !aligned(b->angsleep, 8) || !aligned(b->contact_imp, 8) ||
+        !aligned(b->contact_ab, 4) || !aligned(b->env_state, 16) || !aligned(b->obs, 16) || !aligned(b->rewards, 4) ||
+        (b->targets && !aligned(b->targets, 8)) || (b->tdm_state && !aligned(b->tdm_state, 16)) ||
+        (b->nn_idx && !aligned(b->nn_idx, 4)))
+        return MACM_E_ALIGN;
+    K.posvel = (float4*)b->posvel; K.angsleep = (float2*)b->angsleep; K.fat = (float4*)b->fat;
+    K.c_ab = b->contact_ab; K.c_imp = (float2*)b->contact_imp; K.c_cnt = b->contact_count;
+    K.env_state = (int4*)b->env_state; K.targets = (const float2*)b->targets; K.target_idx = b->target_idx;
+    K.tdm = (float4*)b->tdm_state; K.team = b->team;
+    K.obs = b->obs; K.nn_idx = b->nn_idx; K.rewards = b->rewards; K.collided = b->collided; K.done = b->done;
+    sim->bound = 1;
+    return MACM_OK;
+}
+
+extern "C" int macm_reset(macm_sim* sim, void* stream)
+{
+    if (!sim) return MACM_E_INVALID;
+    if (!sim->bound) return MACM_E_UNBOUND;
+    CU(cudaSetDevice(sim->device));
+    CU(macm_launch_reset(sim->K, (cudaStream_t)stream));
+    CU(macm_launch_observe(sim->K, sim->cfg, (cudaStream_t)stream));
+    sim->launches += 2;
+    return MACM_OK;
+}
+
+extern "C" int macm_sample_reset(macm_sim* sim, uint64_t seed, void* stream)
+{
+    if (!sim) return MACM_E_INVALID;
+    if (!sim->bound) return MACM_E_UNBOUND;
+    const macm_params& p = sim->params;
+    CU(cudaSetDevice(sim->device));
+    CU(macm_launch_sample(sim->K, seed, p.start_spread, p.start_x, p.start_y, p.target_mindist, p.target_maxdist,
+                          p.world_width, p.world_height, (cudaStream_t)stream));
+    sim->launches += 1;
+    return macm_reset(sim, stream);
+}
+
+extern "C" int macm_step(macm_sim* sim, const void* actions, void* stream)
+{
+    if (!sim || !actions) return MACM_E_INVALID;
+    if (!sim->bound) return MACM_E_UNBOUND;
+    if (!aligned(actions, sim->params.action_mode == MACM_ACTION_DISCRETE ? 4 : 8)) return MACM_E_ALIGN;
+    CU(macm_launch_step(sim->K, sim->cfg, actions, (cudaStream_t)stream));
+    sim->launches += 1;
+    return MACM_OK;
+}
+
+extern "C" int macm_observe(macm_sim* sim, void* stream)
+{
+    if (!sim) return MACM_E_INVALID;
+    if (!sim->bound) return MACM_E_UNBOUND;
+    CU(macm_launch_observe(sim->K, sim->cfg, (cudaStream_t)stream));
+    sim->launches += 1;
+    return MACM_OK;
+}
+
+extern "C" int macm_bot_actions(macm_sim* sim, int policy, uint64_t seed, void* actions_out, void* stream)
+{
+    if (!sim || !actions_out) return MACM_E_INVALID;
+    if (!sim->bound) return MACM_E_UNBOUND;
+    if (policy < MACM_BOT_IDLE || policy > MACM_BOT_COMBAT) return MACM_E_INVALID;
+    if (sim->params.action_mode != MACM_ACTION_DISCRETE) return MACM_E_UNSUPPORTED;
+    if (policy == MACM_BOT_COMBAT && sim->K.kind != MACM_ENV_TDM) return MACM_E_INVALID;
+    CU(macm_launch_bot(sim->K, policy, seed, actions_out, (cudaStream_t)stream));
+    sim->launches += 1;
+    return MACM_OK;
+}
+
+extern "C" int macm_step_host(macm_sim* sim, const void* actions, float* obs, float* rewards, int32_t* nn_idx,
+                              uint8_t* collided, uint8_t* done)
+{
+    if (!sim || !actions) return MACM_E_INVALID;
+    if (!sim->bound) return MACM_E_UNBOUND;
+    CU(cudaSetDevice(sim->device));
+    macm_buffer_sizes z;
+    macm_get_buffer_sizes(sim, &z);
+    const size_t abytes = (size_t)sim->K.E * sim->K.N * z.action_bytes;
+    if (!sim->hstream) CU(cudaStreamCreateWithFlags(&sim->hstream, cudaStreamNonBlocking));
+    if (sim->d_actions_bytes < abytes) {
+        if (sim->d_actions) cudaFree(sim->d_actions);
+        sim->d_actions = nullptr;
+        sim->d_actions_bytes = 0;
+        CU(cudaMalloc(&sim->d_actions, abytes));
+        sim->d_actions_bytes = abytes;
+    }
+    cudaStream_t s = sim->hstream;
+    CU(cudaMemcpyAsync(sim->d_actions, actions, abytes, cudaMemcpyHostToDevice, s));
+    CU(macm_launch_step(sim->K, sim->cfg, sim->d_actions, s));
+    sim->launches += 1;
+    if (obs) CU(cudaMemcpyAsync(obs, sim->K.obs, z.obs, cudaMemcpyDeviceToHost, s));
+    if (rewards) CU(cudaMemcpyAsync(rewards, sim->K.rewards, z.rewards, cudaMemcpyDeviceToHost, s));
+    if (nn_idx && sim->K.nn_idx) CU(cudaMemcpyAsync(nn_idx, sim->K.nn_idx, z.nn_idx, cudaMemcpyDeviceToHost, s));
+    if (collided) CU(cudaMemcpyAsync(collided, sim->K.collided, z.collided, cudaMemcpyDeviceToHost, s));
+    if (done) CU(cudaMemcpyAsync(done, sim->K.done, z.done, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return MACM_OK;
+}
+
+extern "C" int macm_host_alloc(void** out, uint64_t bytes)
+{
+    if (!out) return MACM_E_INVALID;
+    return cudaMallocHost(out, bytes) == cudaSuccess ? MACM_OK : MACM_E_CUDA;
+}
+
+extern "C" int macm_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? MACM_OK : MACM_E_CUDA; }
+
+extern "C" int64_t macm_launch_count(const macm_sim* sim) { return sim ? sim->launches : 0; }

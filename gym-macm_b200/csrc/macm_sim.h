@@ -1,0 +1,62 @@
+// Internal definitions shared by the kernels (macm_kernels.cu) and the C-ABI (macm_api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "macm.h"
+
+// b2Settings.h of Box2D 2.3.0 -- the engine pybox2d wraps.
+#define B2_PI 3.14159265359f
+#define B2_EPSILON 1.192092896e-07f
+#define B2_AABB_EXTENSION 0.1f
+#define B2_AABB_MULTIPLIER 2.0f
+#define B2_LINEAR_SLOP 0.005f
+#define B2_MAX_LINEAR_CORRECTION 0.2f
+#define B2_MAX_TRANSLATION 2.0f
+#define B2_BAUMGARTE 0.2f
+#define B2_TIME_TO_SLEEP 0.5f
+#define B2_LINEAR_SLEEP_TOLERANCE 0.01f
+// numpy's float64 pi (mvmnt.py:105-106,114,199)
+#define NP_PI 3.141592653589793
+
+// Kernel argument block (passed by value as a __grid_constant__).
+struct SimConst {
+    int E, N, T, C, TC;
+    int kind, reward_mode, action_mode, coord, vel_iters, pos_iters, warm_starting, flags;
+    int done_step, cd_atk_steps, cd_mov_steps, obs_dim;
+    float h;            // (float)(1/hz): timeStep at the SWIG boundary (cm_framework.py:182,222)
+    float dt_ratio;     // fl(fl(1/h) * h): b2TimeStep::dtRatio once inv_dt0 != 0
+    float inv_mass;     // 1 / (density * b2_pi * r * r)
+    float friction;     // b2MixFriction = sqrtf(f * f)
+    float damp;         // per-step linear damping factor
+    float radius, rsum2;
+    float k_sum, normal_mass;
+    float binary_thr;   // fp32 d^2 threshold equivalent to sqrt64(d2) < reward_radius (mvmnt.py:177)
+    float melee_dmg, init_health;
+    double rot_step;    // agent_rotation_speed * (1/hz)       (mvmnt.py:103-104)
+    double force;       // agent_force                           (mvmnt.py:113-116)
+    double force_pen;   // agent_force * (1 - percent_mov_penalty) (combat.py:46-49)
+    double diag;        // 1/np.sqrt(2)                          (mvmnt.py:112)
+    double melee_range; // combat.py:22,145
+    // state
+    float4* posvel; float2* angsleep; float4* fat;
+    uint32_t* c_ab; float2* c_imp; int* c_cnt; int4* env_state;
+    const float2* targets; const uint8_t* target_idx;
+    float4* tdm; const uint8_t* team;
+    // outputs
+    float* obs; int* nn_idx; float* rewards; uint8_t* collided; uint8_t* done;
+};
+
+struct LaunchCfg {
+    int G, APL, envs_per_block, threads, blocks, smem_bytes;
+};
+
+// implemented in macm_kernels.cu
+cudaError_t macm_launch_cfg(const SimConst& P, LaunchCfg* cfg);
+cudaError_t macm_prepare_kernels(const SimConst& P, const LaunchCfg& cfg, int* blocks_per_sm);
+cudaError_t macm_launch_step(const SimConst& P, const LaunchCfg& cfg, const void* actions, cudaStream_t s);
+cudaError_t macm_launch_observe(const SimConst& P, const LaunchCfg& cfg, cudaStream_t s);
+cudaError_t macm_launch_reset(const SimConst& P, cudaStream_t s);
+cudaError_t macm_launch_sample(const SimConst& P, uint64_t seed, double start_spread, double start_x, double start_y,
+                               double tmin, double tmax, double width, double height, cudaStream_t s);
+cudaError_t macm_launch_bot(const SimConst& P, int policy, uint64_t seed, void* actions_out, cudaStream_t s);

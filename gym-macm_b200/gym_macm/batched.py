@@ -1,0 +1,309 @@
+"""Batched tensor API over libmacm.so: thousands of independent Flock worlds stepped by one kernel.
+
+`BatchedFlock` keeps the reference's surface -- `obs`, `agents`, `done`, `targets`, `settings`,
+`step(actions) -> (obs, rewards)` (gym_macm/envs/mvmnt.py:35-140) -- with torch CUDA tensors
+where the reference has per-agent Python objects.  All simulator state lives in caller-owned
+torch tensors (SoA, env-major) that the C ABI reads and writes in place; this module does no
+arithmetic of its own and has no CPU path.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .settings import combatSettings, flockSettings
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _as_list(n_agents):
+    # the reference wants a list (mvmnt.py:61 `sum(self.n_agents)`); README.md:44 passes an int (App. B4)
+    if isinstance(n_agents, (int, np.integer)):
+        return [int(n_agents)]
+    return [int(x) for x in n_agents]
+
+
+def flock_params(settings, n_envs, n_agents, n_targets):
+    """flockSettings -> macm_params (field-by-field; file:line in include/macm.h)."""
+    p = _lib.default_params(_lib.FLOCK)
+    fx = settings.bodySettings["fixtures"]
+    p.n_envs, p.n_agents, p.n_targets = int(n_envs), int(n_agents), int(n_targets)
+    p.max_contacts, p.max_touching = int(settings.max_contacts), int(settings.max_touching)
+    p.hz = float(settings.hz)
+    p.velocity_iterations = int(settings.velocityIterations)
+    p.position_iterations = int(settings.positionIterations)
+    p.warm_starting = int(bool(settings.enableWarmStarting))
+    p.damping_model = _lib.DAMPING[str(settings.damping_model)]
+    p.radius, p.density, p.friction = float(fx.radius), float(fx.density), float(fx.friction)
+    p.linear_damping = float(settings.bodySettings["linearDamping"])
+    p.agent_force = float(settings.agent_force)
+    p.agent_rotation_speed = float(settings.agent_rotation_speed)
+    p.time_limit = float(settings.time_limit)
+    p.reward_mode = _lib.REWARD[settings.reward_mode]
+    p.action_mode = _lib.ACTION[settings.action_mode]
+    p.coord = _lib.COORD[settings.coord]
+    p.reward_radius = float(settings.reward_radius)
+    p.start_spread = float(settings.start_spread)
+    p.start_x, p.start_y = float(settings.start_point[0]), float(settings.start_point[1])
+    p.target_mindist, p.target_maxdist = float(settings.target_mindist), float(settings.target_maxdist)
+    return p
+
+
+class Engine(object):
+    """A macm_sim handle plus the torch tensors bound to it."""
+
+    _DTYPES = dict(posvel="float32", angsleep="float32", fat="float32", contact_ab="int32", contact_imp="float32",
+                   contact_count="int32", env_state="int32", targets="float32", target_idx="uint8",
+                   tdm_state="float32", team="uint8", obs="float32", nn_idx="int32", rewards="float32",
+                   collided="uint8", done="uint8")
+
+    def __init__(self, params, device=None):
+        torch = _torch()
+        self._h = None
+        L = _lib.lib()  # raises when libmacm.so has not been built
+        if not torch.cuda.is_available():
+            raise _lib.MacmError("gym_macm needs a CUDA device: the simulator is CUDA-only and has no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.MacmError("gym_macm needs a CUDA device, got %r" % (self.device,))
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.params = params
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            torch.cuda.init()
+            _lib.check(L.macm_create(C.byref(h), C.byref(params), self.device.index))
+        self._h = h
+        self.sizes = _lib.MacmBufferSizes()
+        _lib.check(L.macm_get_buffer_sizes(h, C.byref(self.sizes)))
+        self.info = _lib.MacmLaunchInfo()
+        _lib.check(L.macm_get_launch_info(h, C.byref(self.info)))
+        E, N, T = params.n_envs, params.n_agents, params.n_targets
+        Cc, D = self.sizes.max_contacts, self.sizes.obs_dim
+        shapes = dict(posvel=(E, N, 4), angsleep=(E, N, 2), fat=(E, N, 4), contact_ab=(E, Cc), contact_imp=(E, Cc, 2),
+                      contact_count=(E,), env_state=(E, 4), targets=(E, T, 2), target_idx=(N,), tdm_state=(E, N, 4),
+                      team=(N,), obs=(E, N, D), nn_idx=(E, N), rewards=(E, N), collided=(E, N), done=(E,))
+        self.t = {}
+        bufs = _lib.MacmBuffers()
+        for name in _lib.BUFFER_NAMES:
+            nbytes = getattr(self.sizes, name)
+            if nbytes == 0:
+                continue
+            ten = torch.zeros(shapes[name], dtype=getattr(torch, self._DTYPES[name]), device=self.device)
+            assert ten.numel() * ten.element_size() == nbytes, (name, ten.shape, nbytes)
+            self.t[name] = ten
+            setattr(bufs, name, ten.data_ptr())
+        _lib.check(L.macm_bind(h, C.byref(bufs)), h)
+        self.E, self.N, self.T, self.C, self.obs_dim = E, N, T, Cc, D
+        self.action_bytes = self.sizes.action_bytes
+        self._pinned = None
+
+    def close(self):
+        h, self._h = self._h, None
+        if h:
+            _lib.lib().macm_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    def reset(self):
+        _lib.check(_lib.lib().macm_reset(self._h, self._stream()), self._h)
+
+    def sample_reset(self, seed):
+        _lib.check(_lib.lib().macm_sample_reset(self._h, C.c_uint64(int(seed) & (2 ** 64 - 1)), self._stream()), self._h)
+
+    def step(self, actions):
+        _lib.check(_lib.lib().macm_step(self._h, C.c_void_p(actions.data_ptr()), self._stream()), self._h)
+
+    def observe(self):
+        _lib.check(_lib.lib().macm_observe(self._h, self._stream()), self._h)
+
+    def bot_actions(self, policy, seed, out):
+        _lib.check(_lib.lib().macm_bot_actions(self._h, int(policy), C.c_uint64(int(seed) & (2 ** 64 - 1)),
+                                               C.c_void_p(out.data_ptr()), self._stream()), self._h)
+
+    def pinned(self):
+        """Pinned host mirrors of the action input and of every per-step output (for step_host)."""
+        if self._pinned is None:
+            torch = _torch()
+            adt = torch.uint8 if self.action_bytes == 4 else torch.float32
+            ashape = (self.E, self.N, 4) if self.action_bytes == 4 else (self.E, self.N, 2)
+            p = dict(actions=torch.zeros(ashape, dtype=adt).pin_memory())
+            for name in ("obs", "rewards", "nn_idx", "collided", "done"):
+                if name in self.t:
+                    p[name] = torch.zeros(self.t[name].shape, dtype=self.t[name].dtype).pin_memory()
+            self._pinned = p
+        return self._pinned
+
+    def step_host(self, actions_host, want=("obs", "rewards", "nn_idx", "collided", "done")):
+        """macm_step_host: host actions in, host outputs out; the copies are part of the call."""
+        p = self.pinned()
+        if actions_host.data_ptr() != p["actions"].data_ptr():
+            p["actions"].copy_(actions_host)
+        ptr = lambda n: C.c_void_p(p[n].data_ptr()) if (n in want and n in p) else None
+        _lib.check(_lib.lib().macm_step_host(self._h, C.c_void_p(p["actions"].data_ptr()), ptr("obs"), ptr("rewards"),
+                                            ptr("nn_idx"), ptr("collided"), ptr("done")), self._h)
+        return p
+
+    @property
+    def launch_count(self):
+        return int(_lib.lib().macm_launch_count(self._h))
+
+
+class BatchedFlock(object):
+    """E independent Flock environments (gym_macm/envs/mvmnt.py) on one GPU.
+
+    Same constructor keywords as the reference (`n_agents`, `actors`, `colors`, `targets`, any
+    flockSettings attribute) plus `n_envs`, `device`, `seed`.  `obs` keeps the reference's dict
+    keys with tensor values:
+
+        obs["nodes"][0] = {"type": 0, "id": int32 [E,N],  "position": float32 [E,N,2|3]}   nearest agent
+        obs["nodes"][1] = {"type": 1, "id": N,            "position": float32 [E,N,2|3]}   target
+
+    `step(actions)` takes uint8 [E,N,4] (a0,a1,a2,pad) or any integer tensor [E,N,3] on the device
+    (continuous mode: float32 [E,N,2]) and returns `(obs, rewards)` with rewards float32 [E,N].
+    """
+
+    name = "Flock v0 (batched)"
+
+    def __init__(self, n_envs, n_agents=[10], actors=None, colors=None, targets=None, device=None, seed=0, **kwargs):
+        self.settings = flockSettings(**kwargs)
+        self.n_agents = _as_list(n_agents)
+        self.n_envs = int(n_envs)
+        N = sum(self.n_agents)
+        self.n_targets = 1 if targets is None else len(np.unique(targets))
+        # App. B4 repaired: default covers every agent, not just n_agents[0] of them
+        self.targets_idx = [0] * N if targets is None else [int(t) for t in targets]
+        if len(self.targets_idx) != N:
+            raise ValueError("targets must name a target for each of the %d agents" % N)
+        uniq = sorted(set(self.targets_idx))
+        if uniq != list(range(len(uniq))):
+            raise ValueError("targets must use the indices 0..T-1")
+        self.actors, self.colors = actors, colors
+        self.engine = Engine(flock_params(self.settings, self.n_envs, N, self.n_targets), device)
+        torch = _torch()
+        self.engine.t["target_idx"].copy_(torch.tensor(self.targets_idx, dtype=torch.uint8))
+        self.agents = list(range(N))
+        self._act4 = None
+        self.reset(seed)
+
+    # -- state ---------------------------------------------------------------------------------
+    @property
+    def device(self):
+        return self.engine.device
+
+    @property
+    def state(self):
+        """The live state tensors (views, not copies)."""
+        return self.engine.t
+
+    @property
+    def targets(self):
+        return self.engine.t["targets"]
+
+    @property
+    def done(self):
+        return self.engine.t["done"].bool()
+
+    @property
+    def step_count(self):
+        return self.engine.t["env_state"][:, 0]
+
+    @property
+    def time_passed(self):
+        return self.step_count.double() * (1.0 / self.settings.hz)
+
+    def reset(self, seed=0):
+        """Fresh worlds with states drawn on the device from the reference's distributions
+        (mvmnt.py:48-52,62-64).  (The reference's own reset() is broken)"""
+        self.engine.sample_reset(seed)
+        return self.obs
+
+    def load_state(self, pos, angle, vel=None, targets=None):
+        """Create fresh worlds at given positions/angles, like a new b2World with bodies at
+        `pos` (mvmnt.py:70-75): fat AABBs = tight +- 0.1, no contacts, first-step flags."""
+        torch = _torch()
+        t = self.engine.t
+        E, N = self.engine.E, self.engine.N
+        pos = torch.as_tensor(pos, dtype=torch.float32).reshape(E, N, 2)
+        t["posvel"][..., 0:2] = pos.to(self.device)
+        t["posvel"][..., 2:4] = 0 if vel is None else torch.as_tensor(vel, dtype=torch.float32).reshape(E, N, 2).to(self.device)
+        t["angsleep"][..., 0] = torch.as_tensor(angle, dtype=torch.float32).reshape(E, N).to(self.device)
+        if targets is not None:
+            t["targets"].copy_(torch.as_tensor(targets, dtype=torch.float32).reshape(E, self.engine.T, 2))
+        self.engine.reset()
+        return self.obs
+
+    # -- stepping ------------------------------------------------------------------------------
+    @property
+    def obs(self):
+        o, D = self.engine.t["obs"], self.engine.obs_dim // 2
+        return {"nodes": [{"type": 0, "id": self.engine.t["nn_idx"], "position": o[..., 0:D]},
+                          {"type": 1, "id": self.engine.N, "position": o[..., D:2 * D]}]}
+
+    @property
+    def rewards(self):
+        return self.engine.t["rewards"]
+
+    @property
+    def collided(self):
+        return self.engine.t["collided"].bool()
+
+    def pack_actions(self, actions):
+        """Any integer tensor [E,N,3] -> the uint8 [E,N,4] wire format."""
+        torch = _torch()
+        E, N = self.engine.E, self.engine.N
+        if self._act4 is None:
+            self._act4 = torch.zeros((E, N, 4), dtype=torch.uint8, device=self.device)
+        self._act4[..., 0:3] = torch.as_tensor(actions, device=self.device).reshape(E, N, 3)
+        return self._act4
+
+    def step(self, actions):
+        torch = _torch()
+        E, N = self.engine.E, self.engine.N
+        if self.settings.action_mode == "discrete":
+            a = actions
+            if not (torch.is_tensor(a) and a.dtype == torch.uint8 and a.is_cuda and tuple(a.shape) == (E, N, 4)
+                    and a.is_contiguous()):
+                a = self.pack_actions(a)
+        else:
+            a = torch.as_tensor(actions, dtype=torch.float32, device=self.device).reshape(E, N, 2).contiguous()
+        self.engine.step(a)
+        return self.obs, self.engine.t["rewards"]
+
+    def step_host(self, actions):
+        """Same step through the host-buffer entry point (macm_step_host): `actions` is a CPU
+        uint8 [E,N,4] / float32 [E,N,2] tensor; returns pinned CPU tensors."""
+        p = self.engine.step_host(actions)
+        D = self.engine.obs_dim // 2
+        obs = {"nodes": [{"type": 0, "id": p["nn_idx"], "position": p["obs"][..., 0:D]},
+                         {"type": 1, "id": self.engine.N, "position": p["obs"][..., D:2 * D]}]}
+        return obs, p["rewards"]
+
+    def bot_actions(self, policy="flock", seed=0, out=None):
+        """test_scripts/bots.py on the device: one action per agent from the current obs."""
+        torch = _torch()
+        if out is None:
+            out = torch.empty((self.engine.E, self.engine.N, 4), dtype=torch.uint8, device=self.device)
+        self.engine.bot_actions(_lib.BOTS[policy], seed, out)
+        return out
+
+    def contacts(self, env):
+        """Contact list of one env in birth order: (ab [n,2], touching [n], impulses [n,2]) on the CPU."""
+        t = self.engine.t
+        n = int(t["contact_count"][env])
+        ab = t["contact_ab"][env, :n].cpu().numpy().astype(np.uint32)
+        imp = t["contact_imp"][env, :n].cpu().numpy()
+        return np.stack([ab & 0xff, (ab >> 8) & 0xff], -1).astype(np.int32), ((ab >> 16) & 1).astype(np.uint8), imp
+
+    def close(self):
+        self.engine.close()

@@ -1,0 +1,219 @@
+/*
+ * macm.h -- C ABI of libmacm.so: the B200-native batched replacement for the one hot path of
+ * siyarvurucu/gym-macm (per-step Box2D world update + reward pass + observation pass over
+ * thousands of independent environments).
+ *
+ * The reference has no FFI layer of its own: its Python hosts (gym_macm/envs/mvmnt.py,
+ * gym_macm/envs/combat.py, gym_macm/cm_framework.py) drive the pybox2d SWIG module call by
+ * call.  Each entry point below names the reference interface it subsumes (file:line into the
+ * reference tree).  INTEGRATION.md shows the ctypes stub a maintainer adds on the reference
+ * side.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, ints; no C++/torch types.  `stream` is a cudaStream_t passed
+ *     as void* (NULL = the legacy default stream).
+ *   - every pointer in macm_buffers is a DEVICE pointer owned by the caller (the Python host
+ *     allocates them as torch CUDA tensors); the library only keeps the addresses.
+ *   - layout: env-major, agent-minor, fp32/int32/uint8 SoA.  Agent i of env e is element
+ *     e*N + i of every per-agent array.
+ *   - return value: MACM_OK (0) or a negative macm_status; never throws, never exits.
+ *   - no host synchronisation inside macm_step / macm_observe / macm_reset / macm_bot_actions;
+ *     only the *_host convenience calls synchronise (on their own stream).
+ *   - a handle is thread-compatible (one thread at a time), not thread-safe.
+ *   - there is no CPU fallback: without a CUDA device macm_create fails with MACM_E_CUDA.
+ */
+#ifndef MACM_H
+#define MACM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MACM_ABI_VERSION 1
+#define MACM_MAX_AGENTS 64   /* per environment (contact adjacency is a 64-bit row per agent) */
+#define MACM_MAX_TARGETS 16
+#define MACM_MAX_TEAMS 8
+
+typedef enum macm_status {
+    MACM_OK = 0,
+    MACM_E_INVALID = -1,     /* bad argument / parameter out of range */
+    MACM_E_CUDA = -2,        /* a CUDA runtime call failed; see macm_last_cuda_error */
+    MACM_E_UNBOUND = -3,     /* macm_bind has not been called or a required buffer is NULL */
+    MACM_E_ALIGN = -4,       /* a bound buffer is not aligned to its vector width */
+    MACM_E_NOMEM = -5,
+    MACM_E_UNSUPPORTED = -6  /* valid request that this build does not implement */
+} macm_status;
+
+enum { MACM_ENV_FLOCK = 0, MACM_ENV_TDM = 1 };
+enum { MACM_REWARD_BINARY = 0, MACM_REWARD_LINEAR = 1 };
+enum { MACM_ACTION_DISCRETE = 0, MACM_ACTION_CONTINUOUS = 1 };
+enum { MACM_COORD_POLAR = 0, MACM_COORD_CARTESIAN = 1 };
+/* Box2D <= 2.3.0: v *= clamp(1 - h*c, 0, 1);  Box2D >= 2.3.1: v *= 1 / (1 + h*c) */
+enum { MACM_DAMPING_TAYLOR = 0, MACM_DAMPING_PADE = 1 };
+/* macm_params.flags */
+enum {
+    MACM_FLAG_REPAIR_MOV_COOLDOWN = 1 /* cooldown_mov_penalty counts down */
+};
+/* env_state[e][1] bits */
+enum {
+    MACM_ENV_FRESH = 1,           /* world has new fixtures: FindNewContacts runs at the start of the next step */
+    MACM_ENV_CONTACT_OVERFLOW = 2,/* more live contacts than max_contacts: newest were dropped */
+    MACM_ENV_TOUCH_OVERFLOW = 4   /* more touching contacts than max_touching: solver skipped the excess */
+};
+/* scripted actors of test_scripts/bots.py, run on the device by macm_bot_actions */
+enum { MACM_BOT_IDLE = 0, MACM_BOT_FORWARD = 1, MACM_BOT_ROTATE = 2, MACM_BOT_DIAG = 3,
+       MACM_BOT_FLOCK = 4, MACM_BOT_RANDOM = 5, MACM_BOT_COMBAT = 6 };
+
+/*
+ * Everything gym_macm/settings.py and the Agent classes hold that the hot path reads.
+ * Doubles stay doubles because the reference's host arithmetic is Python float64
+ * (mvmnt.py:103-116); the library rounds to fp32 exactly where pybox2d's SWIG layer does.
+ */
+typedef struct macm_params {
+    int32_t env_kind;             /* MACM_ENV_* : Flock (mvmnt.py:27) or TDM (combat.py:56) */
+    int32_t n_envs;               /* independent worlds in the batch */
+    int32_t n_agents;             /* sum(n_agents) of the ctor (mvmnt.py:61), 2..MACM_MAX_AGENTS */
+    int32_t n_targets;            /* len(unique(targets)) (mvmnt.py:42), 1..MACM_MAX_TARGETS; TDM: 0 */
+    int32_t max_contacts;         /* contact capacity per env; 0 = min(N(N-1)/2, 8N) */
+    int32_t max_touching;         /* touching-contact capacity per env (solver staging); 0 = min(max_contacts, 2N) */
+    double hz;                    /* settings.py:30   60.0 */
+    int32_t velocity_iterations;  /* settings.py:31   8 */
+    int32_t position_iterations;  /* settings.py:32   3 */
+    int32_t warm_starting;        /* settings.py:34   1 */
+    int32_t damping_model;        /* MACM_DAMPING_*   (pybox2d's engine version is unpinned) */
+    double radius;                /* settings.py:128  0.5 */
+    double density;               /* settings.py:130  1 */
+    double friction;              /* settings.py:131  0.3 */
+    double linear_damping;        /* settings.py:133  5 */
+    double agent_force;           /* settings.py:124  20 */
+    double agent_rotation_speed;  /* settings.py:123  0.8 * 2 pi */
+    double time_limit;            /* settings.py:125  60 */
+    int32_t reward_mode;          /* settings.py:137 */
+    int32_t action_mode;          /* settings.py:136 */
+    int32_t coord;                /* settings.py:141 */
+    int32_t flags;                /* MACM_FLAG_* */
+    double reward_radius;         /* settings.py:146  7 (binary) */
+    /* TDM only: combat.py:20-24, settings.py:165-166 */
+    double cooldown_atk;          /* 1 */
+    double cooldown_mov_penalty;  /* 0.5 */
+    double melee_range;           /* 2 */
+    double melee_dmg;             /* 0.25 */
+    double percent_mov_penalty;   /* 0.2 */
+    double init_health;           /* 1 */
+    /* initial-state distributions, used only by macm_sample_reset */
+    double start_spread;          /* settings.py:121  20   Flock: pos = spread * (U - 0.5) + start_point */
+    double start_x, start_y;      /* settings.py:122  0, 0 */
+    double target_mindist;        /* settings.py:139  25 */
+    double target_maxdist;        /* settings.py:140  60 */
+    double world_width;           /* combat.py:76     30   TDM: x = U * (team + width/2), y = U * height */
+    double world_height;          /* combat.py:77     30 */
+} macm_params;
+
+/* Caller-owned device buffers.  E = n_envs, N = n_agents, T = n_targets, C = max_contacts. */
+typedef struct macm_buffers {
+    /* ---- state (read and written by macm_step) ---- */
+    float* posvel;            /* [E,N,4] x y vx vy                      16-byte aligned */
+    float* angsleep;          /* [E,N,2] body angle, b2Body::m_sleepTime  8-byte aligned */
+    float* fat;               /* [E,N,4] broadphase fat AABB lo.x lo.y hi.x hi.y  16-byte aligned */
+    uint32_t* contact_ab;     /* [E,C]   a | b<<8 | touching<<16, in BIRTH order (oldest first), a < b */
+    float* contact_imp;       /* [E,C,2] normalImpulse, tangentImpulse (warm start)  8-byte aligned */
+    int32_t* contact_count;   /* [E] */
+    int32_t* env_state;       /* [E,4]   step_count, MACM_ENV_* bits, touching contacts of the last step, winner (TDM; -1)  16-byte aligned */
+    float* targets;           /* [E,T,2] Flock target positions (mvmnt.py:47-52)  8-byte aligned */
+    uint8_t* target_idx;      /* [N]     targets_idx (mvmnt.py:43), shared by all envs */
+    float* tdm_state;         /* [E,N,4] TDM: health, cooldown_atk steps left (int bits), cooldown_mov steps left (int bits), alive (0/1)  16-byte aligned */
+    uint8_t* team;            /* [N]     TDM: team of agent i, shared by all envs */
+    /* ---- outputs (written by macm_step / macm_observe) ---- */
+    float* obs;               /* Flock polar [E,N,4] = nn_dist nn_theta tgt_r tgt_theta;
+                                 Flock cartesian [E,N,6] = nn_dist nn_cos nn_sin tgt_r tgt_cos tgt_sin;
+                                 TDM [E,N,N,4] = r theta phi type(1 ally, 0 enemy, -1 no entry)   16-byte aligned */
+    int32_t* nn_idx;          /* [E,N] id of the nearest other agent (mvmnt.py:187-196); TDM: unused */
+    float* rewards;           /* [E,N] */
+    uint8_t* collided;        /* [E,N] agent appears in some world contact (mvmnt.py:162-164) */
+    uint8_t* done;            /* [E] */
+} macm_buffers;
+
+/* Bytes each macm_buffers member must hold for this sim (0 = not used by this env kind). */
+typedef struct macm_buffer_sizes {
+    uint64_t posvel, angsleep, fat, contact_ab, contact_imp, contact_count, env_state, targets,
+             target_idx, tdm_state, team, obs, nn_idx, rewards, collided, done;
+    int32_t obs_dim;          /* floats per agent in `obs` */
+    int32_t action_bytes;     /* bytes per agent in the `actions` argument of macm_step */
+    int32_t max_contacts, max_touching;
+} macm_buffer_sizes;
+
+/* Launch geometry and derived constants, for benchmarks / DESIGN.md. */
+typedef struct macm_launch_info {
+    int32_t lanes_per_env, agents_per_lane, envs_per_block, threads_per_block, blocks;
+    int32_t smem_bytes_per_block, blocks_per_sm, sm_count;
+    int32_t done_step;        /* first step on which done becomes true (3601 for the defaults, mvmnt.py:134-136) */
+    float dt, dt_ratio, inv_mass, damping_factor, binary_d2_threshold;
+} macm_launch_info;
+
+typedef struct macm_sim macm_sim;
+
+int macm_abi_version(void);
+const char* macm_strerror(int status);
+/* Text of the last CUDA error seen by this handle ("" if none). */
+const char* macm_last_cuda_error(const macm_sim* sim);
+
+/* Fill *p with the reference defaults: flockSettings (settings.py:110-146) or combatSettings
+ * (settings.py:149-175) + combat.Agent constants (combat.py:20-24) + fwSettings (settings.py:25-36). */
+int macm_params_default(macm_params* p, int env_kind);
+
+/* Replaces world construction: NoRender(settings) -> FrameworkBase.__init__ ->
+ * b2World(gravity=(0,0), doSleep=True) (cm_framework.py:155-167) for n_envs worlds at once.
+ * Validates the parameters, derives the fp32 engine constants, selects device `device`.
+ * No device memory is allocated here except the pinned staging of the *_host calls (lazily). */
+int macm_create(macm_sim** out, const macm_params* p, int device);
+int macm_destroy(macm_sim* sim);
+
+int macm_get_buffer_sizes(const macm_sim* sim, macm_buffer_sizes* out);
+int macm_get_launch_info(const macm_sim* sim, macm_launch_info* out);
+int macm_bind(macm_sim* sim, const macm_buffers* buffers);
+
+/* Replaces body creation, world.CreateDynamicBody(**bodySettings, position, angle) for every
+ * agent (mvmnt.py:61-76, combat.py:82-98) plus `self.obs = self.get_obs()` (mvmnt.py:79):
+ * reads posvel (x, y, vx, vy), angsleep.angle, targets; writes fat = tight AABB +- 0.1
+ * (b2_aabbExtension), sleep time 0, no contacts, step_count 0, MACM_ENV_FRESH; TDM: health =
+ * init_health, cool-downs 0, alive 1; then the observation pass. */
+int macm_reset(macm_sim* sim, void* stream);
+
+/* Samples initial states on the device with the reference's distributions (mvmnt.py:48-52,
+ * 62-64; combat.py:84-86) from a counter-based generator keyed by (seed, env, agent), then
+ * does what macm_reset does.  The reference draws from Python's unseeded `random`. */
+int macm_sample_reset(macm_sim* sim, uint64_t seed, void* stream);
+
+/* Replaces one Flock.step / TDM.step for every env (mvmnt.py:81-140, combat.py:104-184):
+ * action decode -> ApplyForce, framework.Step -> b2World::Step(1/hz, velIters, posIters) +
+ * ClearForces (cm_framework.py:213-224), get_rewards (mvmnt.py:160-179), time/done
+ * (mvmnt.py:134-136), get_obs (mvmnt.py:181-222 / combat.py:206-227).
+ * actions (device): discrete uint8 [E,N,4] = a0 a1 a2 a3 (a3: TDM attack bit; Flock ignores it),
+ *                   continuous float [E,N,2]. */
+int macm_step(macm_sim* sim, const void* actions, void* stream);
+
+/* get_obs() alone on the current state (mvmnt.py:181-222 / combat.py:206-227). */
+int macm_observe(macm_sim* sim, void* stream);
+
+/* test_scripts/bots.py on the device: writes one action per agent from the current `obs`
+ * buffer (`actions=None` mode, mvmnt.py:86-92).  MACM_BOT_RANDOM draws U{0,1,2}^3 (x U{0,1})
+ * keyed by (seed, env, agent, step_count). */
+int macm_bot_actions(macm_sim* sim, int policy, uint64_t seed, void* actions_out, void* stream);
+
+/* The drop-in boundary with HOST buffers: copies `actions` host->device, steps, copies
+ * obs / rewards / nn_idx / collided / done device->host (any of the outputs may be NULL) and
+ * waits.  Pinned host memory (macm_host_alloc) makes the copies asynchronous DMA. */
+int macm_step_host(macm_sim* sim, const void* actions, float* obs, float* rewards, int32_t* nn_idx,
+                   uint8_t* collided, uint8_t* done);
+int macm_host_alloc(void** out, uint64_t bytes);
+int macm_host_free(void* p);
+
+/* Number of kernels this handle has launched so far. */
+int64_t macm_launch_count(const macm_sim* sim);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MACM_H */
