@@ -194,7 +194,8 @@ class BatchedFlock(object):
         self.engine.t["target_idx"].copy_(torch.tensor(self.targets_idx, dtype=torch.uint8))
         self.agents = list(range(N))
         self._act4 = None
-        self.reset(seed)
+        if seed is not None:   # seed=None: the caller loads a state itself (load_state)
+            self.reset(seed)
 
     # -- state ---------------------------------------------------------------------------------
     @property

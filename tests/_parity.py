@@ -37,6 +37,8 @@ def compare_step(env, ref, o, k, coord="polar", reward_mode="binary", check_cont
     import torch
     torch.cuda.synchronize()
     E, N = ref.E, ref.N
+    st = env.state
+    assert not (st["env_state"][:, 1].cpu().numpy() & 6).any(), "step %d: contact capacity overflow" % k
     gb, rb = gpu_bodies(env), ref.bodies()
     names = ["x", "y", "vx", "vy", "angle", "sleep", "fat_lx", "fat_ly", "fat_hx", "fat_hy"]
     for c, nm in enumerate(names):
@@ -64,7 +66,6 @@ def compare_step(env, ref, o, k, coord="polar", reward_mode="binary", check_cont
         assert np.array_equal(fl, rfl), "step %d env %d: touching flags" % (k, e)
         t = rfl.astype(bool)
         assert np.array_equal(imp[t], rimp[t]), "step %d env %d: warm-start impulses" % (k, e)
-    assert not (st["env_state"][:, 1].cpu().numpy() & 6).any(), "contact capacity overflow"
     compare_obs(st["obs"].cpu().numpy(), o, coord, k)
 
 
@@ -114,7 +115,8 @@ def run_parity(E, N, steps, targets=None, seed=0, spread=20.0, policy="random", 
     stats = dict(max_contacts=0, max_touching=0, multi=0)
     for k in range(steps):
         if cont:
-            act = rng.uniform(-1, 1, (E, N, 2))
+            # the tensor API takes float32 actions; the oracle gets the same values widened
+            act = rng.uniform(-1.2, 1.2, (E, N, 2)).astype(np.float32).astype(np.float64)
             env.step(torch.as_tensor(act, dtype=torch.float32, device="cuda:0"))
             o = ref.flock_step(act)
         else:

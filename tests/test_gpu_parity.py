@@ -34,7 +34,7 @@ def test_cfg3_multi_flock_targets():
 def test_dense_pile_multi_island_ordering():
     # 64 agents spawned inside 5 m x 5 m: hundreds of touching contacts, bodies with many
     # contacts each -> exercises the island DFS order and the level schedule
-    st = run_parity(16, 64, 40, seed=7, spread=5.0, max_contacts=2016, max_touching=240)
+    st = run_parity(16, 64, 40, seed=7, spread=6.5, max_contacts=2016, max_touching=240)
     assert st["max_touching"] > 64
 
 
