@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- agent-steps/sec of the batched gym-macm step on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] --steps K --warmup W   # the CPU path, timed beside it
+
+Workload (BASELINE.json configs[1]): cm-flock-v0, 64 agents x 4096 envs per GPU, linear reward,
+discrete U{0,1,2}^3 actions, initial states drawn from the reference's distributions.  One "step"
+is one Flock.step for all 4096 envs = one kernel launch.  The footprint of one batch (~20 MB)
+fits in the 126 MB L2, so the timed loop rotates over ROT independent batches (> 2x L2 in
+total): every step's inputs come from HBM.
+
+N > 1 (torchrun, one rank per GPU): each rank owns its own 4096 envs (weak scaling); envs are
+independent, so the data path has no collective.  `--gather` adds the optional NCCL all-gather
+of obs+rewards to every rank (the learner-side exchange of BASELINE config 5).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "gym-macm_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+N_AGENTS, N_ENVS = 64, 4096
+WORKLOAD = "cm-flock-v0 64 agents x 4096 envs per GPU, linear reward, discrete random actions"
+METRIC, UNIT = "agent_steps_per_sec", "agent-steps/s"
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows]
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except Exception:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def b_alg_per_agent_step(c_bar, T, N):
+    # state r/w 40+40, action 4, target index 1, obs 20, reward 4 = 109 B,
+    # + 32 B per live contact per agent (16-byte record read + written), + amortised targets/done
+    return 109.0 + 32.0 * c_bar + (8.0 * T + 1.0) / N
+
+
+def random_state(rng, E, N, T, spread=20.0):
+    """The reference's initial distributions (mvmnt.py:48-52,62-64), as float64 draws."""
+    import numpy as np
+    pos = spread * (rng.random((E, N, 2)) - 0.5)
+    ang = rng.uniform(-1, 1, (E, N)) * np.pi
+    ta = 2 * np.pi * rng.random((E, T))
+    td = 25 + rng.random((E, T)) * 35
+    return pos, ang, np.stack([td * np.cos(ta), td * np.sin(ta)], -1)
+
+
+def cpu_oracle_rate(n_envs, n_threads, budget_s, seed=1234):
+    """agent-steps/s of the CPU oracle (restatement, not pybox2d) on `n_threads` host threads."""
+    import numpy as np
+    from oracle import oracle
+    rng = np.random.default_rng(seed)
+    pos, ang, tg = random_state(rng, n_envs, N_AGENTS, 1)
+    ref = oracle.OracleBatch(n_envs, n_agents=N_AGENTS, n_targets=1, reward_mode=1)
+    ref.reset(pos, ang, targets=tg)
+    acts = rng.integers(0, 3, (8, n_envs, N_AGENTS, 3)).astype(np.int32)
+    for k in range(2):
+        ref.flock_step(acts[k], n_threads)
+    steps, t0 = 0, time.perf_counter()
+    while True:
+        ref.flock_step(acts[steps % 8], n_threads)
+        steps += 1
+        el = time.perf_counter() - t0
+        if el >= budget_s:
+            break
+    return n_envs * N_AGENTS * steps / el, steps, el
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path.  pybox2d cannot be
+    installed (no wheel, no network), so this is the oracle port on every host thread."""
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import oracle
+    oracle.build()
+    cores = len(os.sched_getaffinity(0))
+    sample_envs = 256   # a bounded sample of the 4096-env batch per step
+    rng = np.random.default_rng(1234)
+    pos, ang, tg = random_state(rng, sample_envs, N_AGENTS, 1)
+    ref = oracle.OracleBatch(sample_envs, n_agents=N_AGENTS, n_targets=1, reward_mode=1)
+    ref.reset(pos, ang, targets=tg)
+    acts = rng.integers(0, 3, (16, sample_envs, N_AGENTS, 3)).astype(np.int32)
+    for k in range(args.warmup):
+        ref.flock_step(acts[k % 16], cores)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        ref.flock_step(acts[k % 16], cores)
+    el = time.perf_counter() - t0
+    val = sample_envs * N_AGENTS * args.steps / el
+    sample = "%d of the %d envs per step (x%d agents), %d steps, oracle port on %d threads" % (
+        sample_envs, N_ENVS, N_AGENTS, args.steps, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample,
+                   "note": "pybox2d is not installable here; CPU restatement (oracle/), not pybox2d"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rot", type=int, default=16, help="independent batches rotated through (L2 eviction)")
+    ap.add_argument("--envs", type=int, default=N_ENVS)
+    ap.add_argument("--gather", action="store_true", help="NCCL all-gather of obs+rewards every step")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--e2e-steps", type=int, default=60)
+    ap.add_argument("--policy", default="random", choices=["random", "flock"])
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import gym_macm
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    E, N, ROT = args.envs, N_AGENTS, args.rot
+
+    sims = [gym_macm.BatchedFlock(E, n_agents=[N], reward_mode="linear", device=dev, seed=1234 + 1000 * rank + r)
+            for r in range(ROT)]
+    # U{0,1,2}^3 per agent-step, pre-generated on the device (a pool cycled through)
+    g = torch.Generator(device=dev)
+    g.manual_seed(99 + rank)
+    POOL = 32
+    acts = torch.zeros((POOL, E, N, 4), dtype=torch.uint8, device=dev)
+    acts[..., :3] = torch.randint(0, 3, (POOL, E, N, 3), generator=g, device=dev, dtype=torch.uint8)
+    gathered = None
+    if args.gather and world > 1:
+        gathered = [torch.empty((world,) + tuple(sims[0].state[k].shape), dtype=sims[0].state[k].dtype, device=dev)
+                    for k in ("obs", "rewards")]
+
+    def one_step(k):
+        s = sims[k % ROT]
+        if args.policy == "flock":
+            a = s.bot_actions("flock")
+        else:
+            a = acts[k % POOL]
+        s.engine.step(a)
+        if gathered is not None:
+            dist.all_gather_into_tensor(gathered[0], s.state["obs"])
+            dist.all_gather_into_tensor(gathered[1], s.state["rewards"])
+
+    # settle: every batch takes a few steps so the spawn-time pile-ups are resolved the same way
+    # in all of them, then W warm-up steps of the rotation
+    for k in range(4 * ROT):
+        one_step(k)
+    for k in range(args.warmup):
+        one_step(k)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches0 = sum(s.engine.launch_count for s in sims)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    ev0.record()
+    for k in range(args.steps):
+        one_step(k)
+    ev1.record()
+    torch.cuda.synchronize()
+    t1 = time.time()
+    ms = ev0.elapsed_time(ev1)
+    launches = sum(s.engine.launch_count for s in sims) - launches0
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+    clocks = sampler.stop(t0, t1) if sampler else None
+    ms_per_step = ms / args.steps
+    value = world * E * N * args.steps / (ms * 1e-3)
+
+    # live contacts per agent (c-bar of the roofline formula), measured on this rank's batches
+    c_bar = float(sum(float(s.state["contact_count"].sum()) for s in sims) / (ROT * E * N))
+    touching = float(sum(float(s.state["env_state"][:, 2].sum()) for s in sims) / (ROT * E))
+    b_alg = b_alg_per_agent_step(c_bar, 1, N)
+    peak, peak_kind = measured_peak()
+    achieved = b_alg * E * N / (ms_per_step * 1e-3) / 1e9   # GB/s of ONE GPU's kernel
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    # ---- end to end through the host-buffer entry point (macm_step_host) --------------------
+    e2e = None
+    s0 = sims[0]
+    pin = s0.engine.pinned()
+    host_actions = [acts[i].cpu().pin_memory() for i in range(4)]
+    for k in range(3):
+        s0.engine.step_host(host_actions[k % 4], want=("obs", "rewards", "done"))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    te = time.perf_counter()
+    for k in range(args.e2e_steps):
+        sims[k % ROT].engine.step_host(host_actions[k % 4], want=("obs", "rewards", "done"))
+    el = time.perf_counter() - te
+    if world > 1:
+        t = torch.tensor([el], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        el = float(t.item())
+    h2d = int(host_actions[0].numel() * host_actions[0].element_size())
+    d2h = int(sum(pin[k].numel() * pin[k].element_size() for k in ("obs", "rewards", "done")))
+    e2e = {"value": world * E * N * args.e2e_steps / el, "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
+           "path": "macm_step_host: pinned host actions -> device, step kernel, obs+rewards+done -> pinned host, sync"}
+
+    if rank == 0:
+        cpu = None
+        if world == 1:
+            try:
+                from oracle import oracle
+                oracle.build()
+                cores = len(os.sched_getaffinity(0))
+                n_envs = max(cores * 8, 64)
+                rate, st, el = cpu_oracle_rate(n_envs, cores, args.cpu_seconds)
+                cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                       "sample": "%d envs x %d agents x %d steps in %.1f s; CPU restatement (oracle/), not pybox2d"
+                                 % (n_envs, N, st, el)}
+            except Exception as ex:  # the checker missing must not hide the GPU number
+                cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
+        info = sims[0].engine.info
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "envs_per_gpu": E, "agents_per_env": N, "reward_mode": "linear",
+                       "actions": "pre-generated on device, U{0,1,2}^3" if args.policy == "random" else "bots.flock on device",
+                       "l2": "inputs larger than L2: rotation over %d independent batches (%.0f MB of state+outputs)"
+                             % (ROT, ROT * E * N * 73 / 1e6),
+                       "parallelism": "envs sharded, %d per GPU, no data-path collective%s" % (
+                           E, " + NCCL all-gather of obs/rewards" if gathered is not None else ""),
+                       "launch": {"lanes_per_env": info.lanes_per_env, "agents_per_lane": info.agents_per_lane,
+                                  "threads_per_block": info.threads_per_block, "blocks": info.blocks,
+                                  "smem_per_block": info.smem_bytes_per_block, "blocks_per_sm": info.blocks_per_sm},
+                       "contacts_per_agent": c_bar, "touching_contacts_per_env": touching},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_kind": peak_kind, "bytes_per_agent_step": b_alg,
+                         "kernel": "macm_flock_step_kernel<32,2>", "kernel_ms": ms_per_step},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
