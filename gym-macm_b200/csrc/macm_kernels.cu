@@ -37,12 +37,12 @@ struct Lay {
     static constexpr int ADJL = FHY + 4 * NC, ADJH = ADJL + 4 * NC, NEWL = ADJH + 4 * NC, NEWH = NEWL + 4 * NC;
     static constexpr int ISLMIN = NEWH + 4 * NC;
     static constexpr int LABEL = ISLMIN + 4 * NC, STACK = LABEL + NC, LASTLVL = STACK + NC;
-    static constexpr int ISLACT = LASTLVL + NC, ISLBAD = ISLACT + NC;
-    static constexpr int MISC = (ISLBAD + NC + 15) / 16 * 16;  // 4 x u32
+    static constexpr int ISLACT = LASTLVL + NC, ISLBAD = ISLACT + NC, HEAD = ISLBAD + NC;
+    static constexpr int MISC = (HEAD + NC + 15) / 16 * 16;  // 4 x u32
     static constexpr int FIXED = MISC + 16;
     // per touching contact (capacity TC, a multiple of 16):
-    //   float nx, ny, nI, tI ; u16 slot, ord ; u8 a, b, lvl      = 23 bytes
-    __host__ __device__ static constexpr int bytes(int TC) { return (FIXED + 23 * TC + 15) / 16 * 16; }
+    //   float nx, ny, nI, tI ; u16 slot, ord ; u8 a, b, lvl, nxt_a, nxt_b, taken      = 26 bytes
+    __host__ __device__ static constexpr int bytes(int TC) { return (FIXED + 26 * TC + 15) / 16 * 16; }
 };
 
 struct EnvS {
@@ -76,6 +76,10 @@ struct EnvS {
     template <int NC> __device__ uint8_t* t_a() const { return (uint8_t*)(ord<NC>() + TC); }
     template <int NC> __device__ uint8_t* t_b() const { return t_a<NC>() + TC; }
     template <int NC> __device__ uint8_t* lvl() const { return t_b<NC>() + TC; }
+    template <int NC> __device__ uint8_t* nxt_a() const { return t_b<NC>() + 2 * TC; }
+    template <int NC> __device__ uint8_t* nxt_b() const { return t_b<NC>() + 3 * TC; }
+    template <int NC> __device__ uint8_t* taken() const { return t_b<NC>() + 4 * TC; }
+    template <int NC> __device__ uint8_t* head() const { return base + Lay<NC>::HEAD; }
 };
 
 // ------------------------------------------------------------------------------------------
@@ -520,10 +524,15 @@ __global__ void __launch_bounds__(128) macm_flock_step_kernel(const __grid_const
         S.isl_act<NC>()[i] = 1;
         S.isl_bad<NC>()[i] = 0;
         S.lastlvl<NC>()[i] = 0;
+        S.head<NC>()[i] = 0xff;
     }
     g.sync();
 
     // ---- phase 4: islands (b2World::Solve DFS) -> solve order + levels -------------------------
+    // Box2D seeds islands from the body list (last-created body first), pops a stack, and walks
+    // each body's contact edges newest-first; contacts are solved in the order they are added.
+    // One lane replays exactly that over per-body edge lists (head-inserted in birth order, like
+    // b2ContactManager::AddPair does) and assigns each contact its level on the fly.
     int nlev = tc > 0 ? 1 : 0;
     const bool multi = misc[2] != 0;
     if (tc > 0) {
@@ -540,63 +549,48 @@ __global__ void __launch_bounds__(128) macm_flock_step_kernel(const __grid_const
                 label[b] = (uint8_t)b;
             }
         } else {
-            uint8_t* stack = S.stack<NC>();
-            uint64_t touchb = (uint64_t)misc[0] | ((uint64_t)misc[1] << 32);
-            uint64_t visited = 0;
-            uint32_t taken = 0;  // bit c: the contact this lane looks at in chunk c is in an island
-            int nord = 0;
-            for (int seed = N - 1; seed >= 0; --seed) {
-                if ((visited >> seed) & 1) continue;
-                if (!((touchb >> seed) & 1)) continue;  // singleton island: label stays its own
-                int sp = 0;
-                if (g.gl == 0) stack[0] = (uint8_t)seed;
-                sp = 1;
-                visited |= 1ull << seed;
-                g.sync();
-                while (sp > 0) {
-                    const int b = stack[--sp];
-                    g.sync();
-                    if (g.gl == 0) label[b] = (uint8_t)seed;
-                    // contact edges of b, newest first == touching list backwards
-                    for (int c0 = 0, ch = 0; c0 < tc; c0 += G, ++ch) {
-                        const int t = tc - 1 - (c0 + g.gl);
-                        bool inv = false;
-                        int other = 0;
-                        if (t >= 0 && !((taken >> ch) & 1)) {
-                            const int ta = t_a[t], tb = t_b[t];
-                            inv = (ta == b) || (tb == b);
-                            other = (ta == b) ? tb : ta;
-                        }
-                        const unsigned im = g.ballot(inv);
-                        const bool push = inv && !((visited >> other) & 1);
-                        const unsigned pm = g.ballot(push);
-                        if (inv) {
-                            ord[nord + __popc(im & g.below())] = (uint16_t)t;
-                            taken |= 1u << ch;
-                        }
-                        if (push) stack[sp + __popc(pm & g.below())] = (uint8_t)other;
-                        const unsigned olo = g.reduce_or((push && other < 32) ? (1u << other) : 0u);
-                        const unsigned ohi = g.reduce_or((push && other >= 32) ? (1u << (other - 32)) : 0u);
-                        visited |= (uint64_t)olo | ((uint64_t)ohi << 32);
-                        nord += __popc(im);
-                        sp += __popc(pm);
-                    }
-                    g.sync();
-                }
-            }
-            g.sync();
-            // level schedule of the ordered list (serial, one lane)
             int L = 1;
             if (g.gl == 0) {
-                uint8_t* lastlvl = S.lastlvl<NC>();
-                for (int k = 0; k < tc; ++k) {
-                    const int t = ord[k];
+                uint8_t* stack = S.stack<NC>(); uint8_t* head = S.head<NC>(); uint8_t* lastlvl = S.lastlvl<NC>();
+                uint8_t* nxt_a = S.nxt_a<NC>(); uint8_t* nxt_b = S.nxt_b<NC>(); uint8_t* taken = S.taken<NC>();
+                for (int t = 0; t < tc; ++t) {
                     const int a = t_a[t], b = t_b[t];
-                    const int l = 1 + max((int)lastlvl[a], (int)lastlvl[b]);
-                    lvl[k] = (uint8_t)l;
-                    lastlvl[a] = (uint8_t)l;
-                    lastlvl[b] = (uint8_t)l;
-                    L = max(L, l);
+                    nxt_a[t] = head[a]; head[a] = (uint8_t)t;
+                    nxt_b[t] = head[b]; head[b] = (uint8_t)t;
+                    taken[t] = 0;
+                }
+                // bodies with a touching contact that are not in an island yet
+                uint64_t rem = (uint64_t)misc[0] | ((uint64_t)misc[1] << 32);
+                int nord = 0;
+                while (rem) {
+                    const int seed = 63 - __clzll((long long)rem);
+                    int sp = 0;
+                    stack[sp++] = (uint8_t)seed;
+                    rem &= ~(1ull << seed);
+                    while (sp > 0) {
+                        const int b = stack[--sp];
+                        label[b] = (uint8_t)seed;
+                        for (int t = head[b]; t != 0xff;) {
+                            const int ta = t_a[t], tb = t_b[t];
+                            const int nx = (ta == b) ? nxt_a[t] : nxt_b[t];
+                            if (!taken[t]) {
+                                taken[t] = 1;
+                                ord[nord] = (uint16_t)t;
+                                const int l = 1 + max((int)lastlvl[ta], (int)lastlvl[tb]);
+                                lvl[nord] = (uint8_t)l;
+                                lastlvl[ta] = (uint8_t)l;
+                                lastlvl[tb] = (uint8_t)l;
+                                L = max(L, l);
+                                ++nord;
+                                const int other = (ta == b) ? tb : ta;
+                                if ((rem >> other) & 1) {
+                                    rem &= ~(1ull << other);
+                                    stack[sp++] = (uint8_t)other;
+                                }
+                            }
+                            t = nx;
+                        }
+                    }
                 }
             }
             nlev = g.shfl(L, 0);
@@ -605,6 +599,11 @@ __global__ void __launch_bounds__(128) macm_flock_step_kernel(const __grid_const
     }
 
     // ---- phase 5: contact solver, velocity part -------------------------------------------------
+    // Order position k is owned by lane k % G.  The first G positions (all of them, normally)
+    // live in that lane's registers for the whole solve; later ones go through shared memory.
+    const bool has = g.gl < tc;
+    int ka = 0, kb = 0, klv = 0, kt = 0, kisl = 0;
+    float knx = 1.0f, kny = 0.0f, knI = 0.0f, ktI = 0.0f;
     if (tc > 0) {
         uint8_t* t_a = S.t_a<NC>(); uint8_t* t_b = S.t_b<NC>();
         float* t_nx = S.t_nx<NC>(); float* t_ny = S.t_ny<NC>();
@@ -614,20 +613,37 @@ __global__ void __launch_bounds__(128) macm_flock_step_kernel(const __grid_const
         // b2ContactSolver ctor + InitializeVelocityConstraints: world manifold at the
         // pre-integration positions, impulses scaled by dtRatio
         const float ratio = (es.x == 0) ? 0.0f : P.dt_ratio;  // inv_dt0 == 0 on a world's first step
-        for (int t = g.gl; t < tc; t += G) {
+        for (int k = g.gl; k < tc; k += G) {
+            const int t = ord[k];
             const int a = t_a[t], b = t_b[t];
             float nx = 1.0f, ny = 0.0f;
             const float dx = px[b] - px[a], dy = py[b] - py[a];
             // b2DistanceSquared(pointA, pointB) is (A - B).(A - B); squares are sign-blind
             if ((dx * dx + dy * dy) > B2_EPSILON * B2_EPSILON) { nx = dx; ny = dy; b2normalize(nx, ny); }
-            t_nx[t] = nx; t_ny[t] = ny;
-            if (P.warm_starting) { t_nI[t] = ratio * t_nI[t]; t_tI[t] = ratio * t_tI[t]; }
-            else { t_nI[t] = 0.0f; t_tI[t] = 0.0f; }
+            float nI = 0.0f, tI = 0.0f;
+            if (P.warm_starting) { nI = ratio * t_nI[t]; tI = ratio * t_tI[t]; }
+            if (k < G) {
+                kt = t; ka = a; kb = b; klv = lvl[k]; kisl = label[a];
+                knx = nx; kny = ny; knI = nI; ktI = tI;
+            } else {
+                t_nx[t] = nx; t_ny[t] = ny; t_nI[t] = nI; t_tI[t] = tI;
+            }
         }
-        g.sync();
         if (nlev == 1) {
-            // independent contacts: warm start + all iterations in registers
-            for (int k = g.gl; k < tc; k += G) {
+            // independent contacts: warm start + all iterations without leaving registers
+            if (has) {
+                float vax = vx[ka], vay = vy[ka], vbx = vx[kb], vby = vy[kb];
+                {
+                    const float tx = kny, ty = -knx;
+                    const float Px = knI * knx + ktI * tx, Py = knI * kny + ktI * ty;
+                    vax -= P.inv_mass * Px; vay -= P.inv_mass * Py;
+                    vbx += P.inv_mass * Px; vby += P.inv_mass * Py;
+                }
+                for (int it = 0; it < P.vel_iters; ++it)
+                    solve_velocity(knx, kny, P.friction, mass_n, mass_t, P.inv_mass, knI, ktI, vax, vay, vbx, vby);
+                vx[ka] = vax; vy[ka] = vay; vx[kb] = vbx; vy[kb] = vby;
+            }
+            for (int k = g.gl + G; k < tc; k += G) {
                 const int t = ord[k];
                 const int a = t_a[t], b = t_b[t];
                 const float nx = t_nx[t], ny = t_ny[t];
@@ -648,7 +664,13 @@ __global__ void __launch_bounds__(128) macm_flock_step_kernel(const __grid_const
         } else {
             // WarmStart, in order
             for (int lev = 1; lev <= nlev; ++lev) {
-                for (int k = g.gl; k < tc; k += G) {
+                if (has && klv == lev) {
+                    const float tx = kny, ty = -knx;
+                    const float Px = knI * knx + ktI * tx, Py = knI * kny + ktI * ty;
+                    vx[ka] -= P.inv_mass * Px; vy[ka] -= P.inv_mass * Py;
+                    vx[kb] += P.inv_mass * Px; vy[kb] += P.inv_mass * Py;
+                }
+                for (int k = g.gl + G; k < tc; k += G) {
                     if (lvl[k] != lev) continue;
                     const int t = ord[k];
                     const int a = t_a[t], b = t_b[t];
@@ -662,7 +684,12 @@ __global__ void __launch_bounds__(128) macm_flock_step_kernel(const __grid_const
             }
             for (int it = 0; it < P.vel_iters; ++it) {
                 for (int lev = 1; lev <= nlev; ++lev) {
-                    for (int k = g.gl; k < tc; k += G) {
+                    if (has && klv == lev) {
+                        float vax = vx[ka], vay = vy[ka], vbx = vx[kb], vby = vy[kb];
+                        solve_velocity(knx, kny, P.friction, mass_n, mass_t, P.inv_mass, knI, ktI, vax, vay, vbx, vby);
+                        vx[ka] = vax; vy[ka] = vay; vx[kb] = vbx; vy[kb] = vby;
+                    }
+                    for (int k = g.gl + G; k < tc; k += G) {
                         if (lvl[k] != lev) continue;
                         const int t = ord[k];
                         const int a = t_a[t], b = t_b[t];
@@ -679,7 +706,8 @@ __global__ void __launch_bounds__(128) macm_flock_step_kernel(const __grid_const
         }
         // StoreImpulses -> manifold (next step's warm start)
         uint16_t* t_slot = S.t_slot<NC>();
-        for (int t = g.gl; t < tc; t += G) c_imp[t_slot[t]] = make_float2(t_nI[t], t_tI[t]);
+        if (has) c_imp[t_slot[kt]] = make_float2(knI, ktI);
+        for (int k = g.gl + G; k < tc; k += G) { const int t = ord[k]; c_imp[t_slot[t]] = make_float2(t_nI[t], t_tI[t]); }
     }
 
     // ---- phase 6: integrate positions ------------------------------------------------------------
@@ -711,7 +739,14 @@ __global__ void __launch_bounds__(128) macm_flock_step_kernel(const __grid_const
             uint16_t* ord = S.ord<NC>(); uint8_t* lvl = S.lvl<NC>();
             for (int it = 0; it < P.pos_iters; ++it) {
                 for (int lev = 1; lev <= nlev; ++lev) {
-                    for (int k = g.gl; k < tc; k += G) {
+                    if (has && klv == lev && isl_act[kisl]) {
+                        float cax = px[ka], cay = py[ka], cbx = px[kb], cby = py[kb];
+                        const float sep = solve_position(P.radius, P.k_sum, P.inv_mass, cax, cay, cbx, cby);
+                        px[ka] = cax; py[ka] = cay; px[kb] = cbx; py[kb] = cby;
+                        // island not solved while min(0, separations) < -3 * linearSlop
+                        if (!(b2min(0.0f, sep) >= -3.0f * B2_LINEAR_SLOP)) isl_bad[kisl] = 1;
+                    }
+                    for (int k = g.gl + G; k < tc; k += G) {
                         if (lvl[k] != lev) continue;
                         const int t = ord[k];
                         const int a = t_a[t], b = t_b[t];
@@ -720,7 +755,6 @@ __global__ void __launch_bounds__(128) macm_flock_step_kernel(const __grid_const
                         float cax = px[a], cay = py[a], cbx = px[b], cby = py[b];
                         const float sep = solve_position(P.radius, P.k_sum, P.inv_mass, cax, cay, cbx, cby);
                         px[a] = cax; py[a] = cay; px[b] = cbx; py[b] = cby;
-                        // island not solved while min(0, separations) < -3 * linearSlop
                         if (!(b2min(0.0f, sep) >= -3.0f * B2_LINEAR_SLOP)) isl_bad[isl] = 1;
                     }
                     g.sync();
