@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--e2e-steps", type=int, default=60)
     ap.add_argument("--policy", default="random", choices=["random", "flock"])
+    ap.add_argument("--settle", type=int, default=64, help="untimed steps per batch after the random spawn")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -195,7 +196,7 @@ def main():
     # U{0,1,2}^3 per agent-step, pre-generated on the device (a pool cycled through)
     g = torch.Generator(device=dev)
     g.manual_seed(99 + rank)
-    POOL = 32
+    POOL = 61   # prime: batch r at its j-th step uses action set (j + 7 r) mod POOL, all distinct in sequence
     acts = torch.zeros((POOL, E, N, 4), dtype=torch.uint8, device=dev)
     acts[..., :3] = torch.randint(0, 3, (POOL, E, N, 3), generator=g, device=dev, dtype=torch.uint8)
     gathered = None
@@ -208,15 +209,15 @@ def main():
         if args.policy == "flock":
             a = s.bot_actions("flock")
         else:
-            a = acts[k % POOL]
+            a = acts[(k // ROT + 7 * (k % ROT)) % POOL]
         s.engine.step(a)
         if gathered is not None:
             dist.all_gather_into_tensor(gathered[0], s.state["obs"])
             dist.all_gather_into_tensor(gathered[1], s.state["rewards"])
 
-    # settle: every batch takes a few steps so the spawn-time pile-ups are resolved the same way
-    # in all of them, then W warm-up steps of the rotation
-    for k in range(4 * ROT):
+    # settle: every batch runs SETTLE steps (1.07 s of simulated time of a 60 s / 3601-step episode)
+    # so that the overlaps of the random spawn are resolved; then W warm-up steps of the rotation
+    for k in range(args.settle * ROT):
         one_step(k)
     for k in range(args.warmup):
         one_step(k)
@@ -310,6 +311,7 @@ def main():
                        "launch": {"lanes_per_env": info.lanes_per_env, "agents_per_lane": info.agents_per_lane,
                                   "threads_per_block": info.threads_per_block, "blocks": info.blocks,
                                   "smem_per_block": info.smem_bytes_per_block, "blocks_per_sm": info.blocks_per_sm},
+                       "settle_steps_per_batch": args.settle,
                        "contacts_per_agent": c_bar, "touching_contacts_per_env": touching},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -24,6 +24,7 @@ struct macm_sim {
     cudaStream_t hstream;
     void* d_actions;
     size_t d_actions_bytes;
+    double2* d_sincos;
 };
 
 static int fail_cuda(macm_sim* s, cudaError_t e, const char* where)
@@ -170,6 +171,7 @@ static int derive_constants(macm_sim* sim)
     K.diag = 1 / sqrt(2.0);
     K.melee_range = p.melee_range;
     K.melee_dmg = (float)p.melee_dmg;
+    K.melee_dmg_d = p.melee_dmg;
     K.init_health = (float)p.init_health;
     K.cd_atk_steps = cooldown_steps(p.cooldown_atk, p.hz);
     K.cd_mov_steps = cooldown_steps(p.cooldown_mov_penalty, p.hz);
@@ -189,7 +191,6 @@ extern "C" int macm_create(macm_sim** out, const macm_params* p, int device)
     if (p->reward_mode < 0 || p->reward_mode > 1 || p->action_mode < 0 || p->action_mode > 1 || p->coord < 0 ||
         p->coord > 1 || p->damping_model < 0 || p->damping_model > 1)
         return MACM_E_INVALID;
-    if (p->env_kind == MACM_ENV_TDM) return MACM_E_UNSUPPORTED;  // TODO(round 1): TDM kernel
 
     macm_sim* sim = new (std::nothrow) macm_sim;
     if (!sim) return MACM_E_NOMEM;
@@ -212,6 +213,15 @@ extern "C" int macm_create(macm_sim** out, const macm_params* p, int device)
     e = macm_launch_cfg(sim->K, &sim->cfg);
     if (e != cudaSuccess) { *out = nullptr; delete sim; return MACM_E_INVALID; }
     CU(macm_prepare_kernels(sim->K, sim->cfg, &sim->blocks_per_sm));
+    // sin/cos(k/128), k = 0..417, as float64: the table behind the action decode's np.cos/np.sin
+    {
+        const int n = 418;
+        double2 tab[n];
+        for (int k = 0; k < n; ++k) { tab[k].x = sin(k * 0.0078125); tab[k].y = cos(k * 0.0078125); }
+        CU(cudaMalloc((void**)&sim->d_sincos, sizeof(tab)));
+        CU(cudaMemcpy(sim->d_sincos, tab, sizeof(tab), cudaMemcpyHostToDevice));
+        sim->K.sincos_tab = sim->d_sincos;
+    }
     return MACM_OK;
 }
 
@@ -220,6 +230,7 @@ extern "C" int macm_destroy(macm_sim* sim)
     if (!sim) return MACM_E_INVALID;
     cudaSetDevice(sim->device);
     if (sim->d_actions) cudaFree(sim->d_actions);
+    if (sim->d_sincos) cudaFree(sim->d_sincos);
     if (sim->hstream) cudaStreamDestroy(sim->hstream);
     delete sim;
     return MACM_OK;
@@ -347,6 +358,7 @@ extern "C" int macm_step_host(macm_sim* sim, const void* actions, float* obs, fl
     if (!sim->hstream) CU(cudaStreamCreateWithFlags(&sim->hstream, cudaStreamNonBlocking));
     if (sim->d_actions_bytes < abytes) {
         if (sim->d_actions) cudaFree(sim->d_actions);
+    if (sim->d_sincos) cudaFree(sim->d_sincos);
         sim->d_actions = nullptr;
         sim->d_actions_bytes = 0;
         CU(cudaMalloc(&sim->d_actions, abytes));

@@ -32,54 +32,54 @@ namespace {
 // ------------------------------------------------------------------------------------------
 template <int NC>
 struct Lay {
-    static constexpr int PX = 0, PY = PX + 4 * NC, VX = PY + 4 * NC, VY = VX + 4 * NC;
-    static constexpr int FLX = VY + 4 * NC, FLY = FLX + 4 * NC, FHX = FLY + 4 * NC, FHY = FHX + 4 * NC;
-    static constexpr int ADJL = FHY + 4 * NC, ADJH = ADJL + 4 * NC, NEWL = ADJH + 4 * NC, NEWH = NEWL + 4 * NC;
-    static constexpr int ISLMIN = NEWH + 4 * NC;
-    static constexpr int LABEL = ISLMIN + 4 * NC, STACK = LABEL + NC, LASTLVL = STACK + NC;
-    static constexpr int ISLACT = LASTLVL + NC, ISLBAD = ISLACT + NC, HEAD = ISLBAD + NC;
+    static constexpr int POS = 0;                 // float2 [NC]  centre
+    static constexpr int VEL = POS + 8 * NC;      // float2 [NC]  linear velocity
+    static constexpr int FAT = VEL + 8 * NC;      // float4 [NC]  fat AABB lo.xy hi.xy
+    static constexpr int ADJ = FAT + 16 * NC;     // uint2  [NC]  contact adjacency row (agents 0-31, 32-63)
+    static constexpr int NEW = ADJ + 8 * NC;      // uint2  [NC]  new-pair row being assembled / float4 ray (TDM)
+    static constexpr int ISLMIN = NEW + 8 * NC;   // u32    [NC]  min sleep time of the island seeded here
+    static constexpr int ANG = ISLMIN + 4 * NC;   // float  [NC]  body angle (TDM observation pass)
+    static constexpr int LABEL = ANG + 4 * NC;    // u8     [NC]  island seed of a body
+    static constexpr int STACK = LABEL + NC, LASTLVL = STACK + NC, ISLACT = LASTLVL + NC, ISLBAD = ISLACT + NC;
+    static constexpr int HEAD = ISLBAD + NC;      // u8     [NC]  newest touching contact of a body
     static constexpr int MISC = (HEAD + NC + 15) / 16 * 16;  // 4 x u32
     static constexpr int FIXED = MISC + 16;
     // per touching contact (capacity TC, a multiple of 16):
-    //   float nx, ny, nI, tI ; u16 slot, ord ; u8 a, b, lvl, nxt_a, nxt_b, taken      = 26 bytes
-    __host__ __device__ static constexpr int bytes(int TC) { return (FIXED + 26 * TC + 15) / 16 * 16; }
+    //   float2 normal ; float2 impulses ; u32 edge word ; u16 slot ; u16 ord|lvl<<8    = 24 bytes
+    __host__ __device__ static constexpr int bytes(int TC) { return (FIXED + 24 * TC + 15) / 16 * 16; }
 };
 
+// edge word of a touching contact: a | b<<6 | next-of-a<<12 | next-of-b<<20 | taken<<28
+#define EW_A(w) ((int)((w) & 63u))
+#define EW_B(w) ((int)(((w) >> 6) & 63u))
+#define EW_NA(w) ((int)(((w) >> 12) & 255u))
+#define EW_NB(w) ((int)(((w) >> 20) & 255u))
+#define EW_TAKEN 0x10000000u
+#define EW_NONE 255
+
+template <int NC>
 struct EnvS {
     unsigned char* base;
     int TC;
-    template <int NC> __device__ float* px() const { return (float*)(base + Lay<NC>::PX); }
-    template <int NC> __device__ float* py() const { return (float*)(base + Lay<NC>::PY); }
-    template <int NC> __device__ float* vx() const { return (float*)(base + Lay<NC>::VX); }
-    template <int NC> __device__ float* vy() const { return (float*)(base + Lay<NC>::VY); }
-    template <int NC> __device__ float* flx() const { return (float*)(base + Lay<NC>::FLX); }
-    template <int NC> __device__ float* fly() const { return (float*)(base + Lay<NC>::FLY); }
-    template <int NC> __device__ float* fhx() const { return (float*)(base + Lay<NC>::FHX); }
-    template <int NC> __device__ float* fhy() const { return (float*)(base + Lay<NC>::FHY); }
-    template <int NC> __device__ uint32_t* adj_lo() const { return (uint32_t*)(base + Lay<NC>::ADJL); }
-    template <int NC> __device__ uint32_t* adj_hi() const { return (uint32_t*)(base + Lay<NC>::ADJH); }
-    template <int NC> __device__ uint32_t* new_lo() const { return (uint32_t*)(base + Lay<NC>::NEWL); }
-    template <int NC> __device__ uint32_t* new_hi() const { return (uint32_t*)(base + Lay<NC>::NEWH); }
-    template <int NC> __device__ uint32_t* isl_min() const { return (uint32_t*)(base + Lay<NC>::ISLMIN); }
-    template <int NC> __device__ uint8_t* label() const { return base + Lay<NC>::LABEL; }
-    template <int NC> __device__ uint8_t* stack() const { return base + Lay<NC>::STACK; }
-    template <int NC> __device__ uint8_t* lastlvl() const { return base + Lay<NC>::LASTLVL; }
-    template <int NC> __device__ uint8_t* isl_act() const { return base + Lay<NC>::ISLACT; }
-    template <int NC> __device__ uint8_t* isl_bad() const { return base + Lay<NC>::ISLBAD; }
-    template <int NC> __device__ uint32_t* misc() const { return (uint32_t*)(base + Lay<NC>::MISC); }
-    template <int NC> __device__ float* t_nx() const { return (float*)(base + Lay<NC>::FIXED); }
-    template <int NC> __device__ float* t_ny() const { return t_nx<NC>() + TC; }
-    template <int NC> __device__ float* t_nI() const { return t_nx<NC>() + 2 * TC; }
-    template <int NC> __device__ float* t_tI() const { return t_nx<NC>() + 3 * TC; }
-    template <int NC> __device__ uint16_t* t_slot() const { return (uint16_t*)(t_nx<NC>() + 4 * TC); }
-    template <int NC> __device__ uint16_t* ord() const { return t_slot<NC>() + TC; }
-    template <int NC> __device__ uint8_t* t_a() const { return (uint8_t*)(ord<NC>() + TC); }
-    template <int NC> __device__ uint8_t* t_b() const { return t_a<NC>() + TC; }
-    template <int NC> __device__ uint8_t* lvl() const { return t_b<NC>() + TC; }
-    template <int NC> __device__ uint8_t* nxt_a() const { return t_b<NC>() + 2 * TC; }
-    template <int NC> __device__ uint8_t* nxt_b() const { return t_b<NC>() + 3 * TC; }
-    template <int NC> __device__ uint8_t* taken() const { return t_b<NC>() + 4 * TC; }
-    template <int NC> __device__ uint8_t* head() const { return base + Lay<NC>::HEAD; }
+    __device__ float2* pos() const { return (float2*)(base + Lay<NC>::POS); }
+    __device__ float2* vel() const { return (float2*)(base + Lay<NC>::VEL); }
+    __device__ float4* fat() const { return (float4*)(base + Lay<NC>::FAT); }
+    __device__ uint2* adj() const { return (uint2*)(base + Lay<NC>::ADJ); }
+    __device__ uint2* nw() const { return (uint2*)(base + Lay<NC>::NEW); }
+    __device__ uint32_t* isl_min() const { return (uint32_t*)(base + Lay<NC>::ISLMIN); }
+    __device__ float* ang() const { return (float*)(base + Lay<NC>::ANG); }
+    __device__ uint8_t* label() const { return base + Lay<NC>::LABEL; }
+    __device__ uint8_t* stack() const { return base + Lay<NC>::STACK; }
+    __device__ uint8_t* lastlvl() const { return base + Lay<NC>::LASTLVL; }
+    __device__ uint8_t* isl_act() const { return base + Lay<NC>::ISLACT; }
+    __device__ uint8_t* isl_bad() const { return base + Lay<NC>::ISLBAD; }
+    __device__ uint8_t* head() const { return base + Lay<NC>::HEAD; }
+    __device__ uint32_t* misc() const { return (uint32_t*)(base + Lay<NC>::MISC); }
+    __device__ float2* t_n() const { return (float2*)(base + Lay<NC>::FIXED); }
+    __device__ float2* t_imp() const { return t_n() + TC; }
+    __device__ uint32_t* t_ew() const { return (uint32_t*)(t_n() + 2 * TC); }
+    __device__ uint16_t* t_slot() const { return (uint16_t*)(t_ew() + TC); }
+    __device__ uint16_t* ordlvl() const { return t_slot() + TC; }
 };
 
 // ------------------------------------------------------------------------------------------
@@ -99,9 +99,7 @@ struct Grp {
     __device__ unsigned ballot(bool p) const { return (__ballot_sync(mask, p) & mask) >> shift; }
     __device__ void sync() const { __syncwarp(mask); }
     __device__ unsigned below() const { return (1u << gl) - 1u; }
-    __device__ unsigned reduce_or(unsigned v) const { return __reduce_or_sync(mask, v); }
     __device__ unsigned reduce_min(unsigned v) const { return __reduce_min_sync(mask, v); }
-    __device__ unsigned reduce_max(unsigned v) const { return __reduce_max_sync(mask, v); }
     __device__ int shfl(int v, int src) const { return __shfl_sync(mask, v, shift + src); }
     // inclusive prefix sum over the group lanes
     __device__ int scan_incl(int v) const
@@ -115,12 +113,18 @@ struct Grp {
     }
 };
 
+// 64-bit agent sets as two words: agent i -> word i >> 5, bit i & 31 (slot s of a 32-lane group is word s)
+__device__ __forceinline__ bool bit_of(uint2 m, int i) { return (((i < 32) ? m.x : m.y) >> (i & 31)) & 1u; }
+__device__ __forceinline__ void or_bit(uint2* row, int r, int bit)
+{
+    atomicOr(bit < 32 ? &row[r].x : &row[r].y, 1u << (bit & 31));
+}
+
 // b2TestOverlap(b2AABB, b2AABB): d1 = b.lo - a.hi, d2 = a.lo - b.hi; overlap iff no component > 0.
 // With IEEE gradual underflow (no -ftz) x - y > 0 <=> x > y, so the subtractions are not needed.
-__device__ __forceinline__ bool aabb_overlap(float alx, float aly, float ahx, float ahy, float blx, float bly,
-                                             float bhx, float bhy)
+__device__ __forceinline__ bool aabb_overlap(const float4 a, const float4 b)
 {
-    return !(blx > ahx || bly > ahy || alx > bhx || aly > bhy);
+    return !(b.x > a.z || b.y > a.w || a.x > b.z || a.y > b.w);
 }
 
 __device__ __forceinline__ float b2min(float a, float b) { return a < b ? a : b; }
@@ -145,15 +149,33 @@ __device__ __forceinline__ float wrap_pi_f(float t)
     return t;
 }
 
+// sin and cos of a float32 angle to ~1 ulp of float64.  A = k/128 + x with |x| <= 2^-8 (exact
+// split, A is a float): table of sin/cos(k/128) (host-computed doubles) + degree-7/8 Taylor.
+// Outside the table (|A| > 3.25, only reachable through load_state) falls back to sincos().
+__device__ __forceinline__ void sincos_f32arg(const double2* __restrict__ tab, float Af, double& s, double& c)
+{
+    const float fk = rintf(fabsf(Af) * 128.0f);
+    if (!(fk <= 416.0f)) { sincos((double)Af, &s, &c); return; }
+    const double2 sc = __ldg(&tab[(int)fk]);
+    const double x = fabs((double)Af) - (double)fk * 0.0078125;
+    const double x2 = x * x;
+    // sin x = x + x^3 (-1/6 + x^2 (1/120 - x^2/5040)) ; cos x - 1 = x^2 (-1/2 + x^2 (1/24 + x^2 (-1/720 + x^2/40320)))
+    const double ps = fma(x2, fma(x2, -1.984126984126984e-04, 8.333333333333333e-03), -1.6666666666666666e-01);
+    const double sl = fma(x * x2, ps, x);
+    const double dc = x2 * fma(x2, fma(x2, fma(x2, 2.48015873015873e-05, -1.388888888888889e-03), 4.1666666666666664e-02), -0.5);
+    const double sa = sc.x + fma(sc.y, sl, sc.x * dc);
+    c = sc.y + fma(sc.y, dc, -(sc.x * sl));
+    s = (Af < 0.0f) ? -sa : sa;
+}
+
 // One velocity-constraint pass of one contact (b2ContactSolver::SolveVelocityConstraints,
 // pointCount == 1, invI = 0): tangent (friction) first, then normal.
 __device__ __forceinline__ void solve_velocity(float nx, float ny, float friction, float mass_n, float mass_t,
-                                               float inv_mass, float& nI, float& tI, float& vax, float& vay,
-                                               float& vbx, float& vby)
+                                               float inv_mass, float& nI, float& tI, float2& va, float2& vb)
 {
     const float tx = ny, ty = -nx;  // b2Cross(normal, 1.0f)
     {
-        float dvx = vbx - vax, dvy = vby - vay;
+        float dvx = vb.x - va.x, dvy = vb.y - va.y;
         float vt = dvx * tx + dvy * ty;
         float lambda = mass_t * (-vt);
         float maxf = friction * nI;
@@ -161,48 +183,50 @@ __device__ __forceinline__ void solve_velocity(float nx, float ny, float frictio
         lambda = ni - tI;
         tI = ni;
         float Px = lambda * tx, Py = lambda * ty;
-        vax -= inv_mass * Px; vay -= inv_mass * Py;
-        vbx += inv_mass * Px; vby += inv_mass * Py;
+        va.x -= inv_mass * Px; va.y -= inv_mass * Py;
+        vb.x += inv_mass * Px; vb.y += inv_mass * Py;
     }
     {
-        float dvx = vbx - vax, dvy = vby - vay;
+        float dvx = vb.x - va.x, dvy = vb.y - va.y;
         float vn = dvx * nx + dvy * ny;
         float lambda = -mass_n * vn;
         float ni = b2max(nI + lambda, 0.0f);
         lambda = ni - nI;
         nI = ni;
         float Px = lambda * nx, Py = lambda * ny;
-        vax -= inv_mass * Px; vay -= inv_mass * Py;
-        vbx += inv_mass * Px; vby += inv_mass * Py;
+        va.x -= inv_mass * Px; va.y -= inv_mass * Py;
+        vb.x += inv_mass * Px; vb.y += inv_mass * Py;
     }
+}
+
+// b2ContactSolver::WarmStart of one contact
+__device__ __forceinline__ void warm_start(float nx, float ny, float nI, float tI, float inv_mass, float2& va, float2& vb)
+{
+    const float tx = ny, ty = -nx;
+    const float Px = nI * nx + tI * tx, Py = nI * ny + tI * ty;
+    va.x -= inv_mass * Px; va.y -= inv_mass * Py;
+    vb.x += inv_mass * Px; vb.y += inv_mass * Py;
 }
 
 // One position-constraint pass of one contact (b2ContactSolver::SolvePositionConstraints +
 // b2PositionSolverManifold::Initialize, e_circles).  Returns the separation it saw.
-__device__ __forceinline__ float solve_position(float radius, float k_sum, float inv_mass, float& cax, float& cay,
-                                                float& cbx, float& cby)
+__device__ __forceinline__ float solve_position(float radius, float k_sum, float inv_mass, float2& ca, float2& cb)
 {
-    float nx = cbx - cax, ny = cby - cay;
+    float nx = cb.x - ca.x, ny = cb.y - ca.y;
     const float dx = nx, dy = ny;
     b2normalize(nx, ny);
     float sep = (dx * nx + dy * ny) - radius - radius;
     float C = b2clamp(B2_BAUMGARTE * (sep + B2_LINEAR_SLOP), -B2_MAX_LINEAR_CORRECTION, 0.0f);
     float imp = k_sum > 0.0f ? -C / k_sum : 0.0f;
     float Px = imp * nx, Py = imp * ny;
-    cax -= inv_mass * Px; cay -= inv_mass * Py;
-    cbx += inv_mass * Px; cby += inv_mass * Py;
+    ca.x -= inv_mass * Px; ca.y -= inv_mass * Py;
+    cb.x += inv_mass * Px; cb.y += inv_mass * Py;
     return sep;
-}
-
-__device__ __forceinline__ void set_bit64(uint32_t* lo, uint32_t* hi, int row, int bit)
-{
-    if (bit < 32) atomicOr(&lo[row], 1u << bit);
-    else atomicOr(&hi[row], 1u << (bit - 32));
 }
 
 // ------------------------------------------------------------------------------------------
 // b2ContactManager::FindNewContacts for one environment (group-cooperative).
-//   moved: 64-bit mask of proxies in the broadphase move buffer.
+//   moved: set of proxies in the broadphase move buffer.
 //   Every other proxy whose fat AABB overlaps a moved one forms a pair; pairs are sorted
 //   lexicographically, de-duplicated, and those without a contact yet are created in that
 //   order (lower index = fixtureA).  Here: row i of a bit matrix holds the partners j > i;
@@ -210,32 +234,36 @@ __device__ __forceinline__ void set_bit64(uint32_t* lo, uint32_t* hi, int row, i
 // Appends to the HBM contact list at `cnt`; returns the new count (uniform over the group).
 // ------------------------------------------------------------------------------------------
 template <int G, int APL>
-__device__ int find_new_contacts(const Grp<G>& g, const EnvS& S, const SimConst& P, uint64_t moved, uint64_t alive,
+__device__ int find_new_contacts(const Grp<G>& g, const EnvS<G * APL>& S, const SimConst& P, uint2 moved, uint2 alive,
                                  int cnt, uint32_t* c_ab, float2* c_imp, bool& overflow)
 {
-    constexpr int NC = G * APL;
-    float* flx = S.flx<NC>(); float* fly = S.fly<NC>(); float* fhx = S.fhx<NC>(); float* fhy = S.fhy<NC>();
-    uint32_t* adj_lo = S.adj_lo<NC>(); uint32_t* adj_hi = S.adj_hi<NC>();
-    uint32_t* new_lo = S.new_lo<NC>(); uint32_t* new_hi = S.new_hi<NC>();
+    const float4* fat = S.fat();
+    uint2* adj = S.adj();
+    uint2* nw = S.nw();
 
-    uint64_t hit[APL];
-    float olx[APL], oly[APL], ohx[APL], ohy[APL];
+    uint2 hit[APL];
+    float4 own[APL];
 #pragma unroll
     for (int s = 0; s < APL; ++s) {
         const int i = g.gl + s * G;
-        hit[s] = 0;
-        olx[s] = flx[i]; oly[s] = fly[i]; ohx[s] = fhx[i]; ohy[s] = fhy[i];
-        new_lo[i] = 0; new_hi[i] = 0;
+        hit[s] = make_uint2(0u, 0u);
+        own[s] = fat[i];
+        // dead / padding agents have no proxy: park their box where nothing overlaps it
+        if (!bit_of(alive, i)) own[s] = make_float4(3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f);
+        nw[i] = make_uint2(0u, 0u);
     }
     g.sync();
-    for (uint64_t mm = moved; mm; mm &= mm - 1) {
-        const int m = __ffsll((long long)mm) - 1;
-        const float mlx = flx[m], mly = fly[m], mhx = fhx[m], mhy = fhy[m];
 #pragma unroll
-        for (int s = 0; s < APL; ++s) {
-            const int i = g.gl + s * G;
-            if (i != m && ((alive >> i) & 1) && aabb_overlap(mlx, mly, mhx, mhy, olx[s], oly[s], ohx[s], ohy[s]))
-                hit[s] |= 1ull << m;
+    for (int w = 0; w < (G * APL + 31) / 32; ++w) {
+        for (unsigned mm = w ? moved.y : moved.x; mm; mm &= mm - 1) {
+            const int m = w * 32 + __ffs((int)mm) - 1;
+            const float4 mb = fat[m];
+            const unsigned bit = 1u << (m & 31);
+#pragma unroll
+            for (int s = 0; s < APL; ++s) {
+                const bool h = (g.gl + s * G != m) && aabb_overlap(mb, own[s]);
+                if (w == 0) hit[s].x |= h ? bit : 0u; else hit[s].y |= h ? bit : 0u;
+            }
         }
     }
     // pair (m, i) with m < i belongs to row m: the owner of m finds it itself iff i moved too;
@@ -243,38 +271,49 @@ __device__ int find_new_contacts(const Grp<G>& g, const EnvS& S, const SimConst&
 #pragma unroll
     for (int s = 0; s < APL; ++s) {
         const int i = g.gl + s * G;
-        if (!((moved >> i) & 1)) {
-            uint64_t low = hit[s] & ((1ull << i) - 1ull);
-            for (; low; low &= low - 1) {
-                const int m = __ffsll((long long)low) - 1;
-                set_bit64(new_lo, new_hi, m, i);
-            }
+        if (!bit_of(moved, i)) {
+            unsigned lo = hit[s].x, hi = hit[s].y;
+            if (i < 32) { lo &= (1u << i) - 1u; hi = 0u; } else { hi &= (1u << (i - 32)) - 1u; }
+            for (; lo; lo &= lo - 1) or_bit(nw, __ffs((int)lo) - 1, i);
+            for (; hi; hi &= hi - 1) or_bit(nw, 32 + __ffs((int)hi) - 1, i);
         }
     }
     g.sync();
-    uint64_t fresh[APL];
+    uint2 fresh[APL];
+    bool any = false;
+#pragma unroll
+    for (int s = 0; s < APL; ++s) {
+        const int i = g.gl + s * G;
+        uint2 row = hit[s];
+        // keep partners j > i only
+        if (i < 32) row.x &= ~((2u << i) - 1u); else { row.x = 0u; row.y &= ~((2u << (i - 32)) - 1u); }
+        const uint2 posted = nw[i], have = adj[i];
+        fresh[s] = make_uint2((row.x | posted.x) & ~have.x, (row.y | posted.y) & ~have.y);
+        any |= (fresh[s].x | fresh[s].y) != 0u;
+    }
+    if (!g.ballot(any)) return cnt;
     int base = cnt;
 #pragma unroll
     for (int s = 0; s < APL; ++s) {
         const int i = g.gl + s * G;
-        uint64_t row = (hit[s] & ~((2ull << i) - 1ull)) | ((uint64_t)new_lo[i] | ((uint64_t)new_hi[i] << 32));
-        uint64_t have = (uint64_t)adj_lo[i] | ((uint64_t)adj_hi[i] << 32);
-        fresh[s] = row & ~have;
-        const int c = __popcll(fresh[s]);
+        const int c = __popc(fresh[s].x) + __popc(fresh[s].y);
         const int incl = g.scan_incl(c);
         const int total = g.shfl(incl, G - 1);
         int pos = base + incl - c;
-        for (uint64_t f = fresh[s]; f; f &= f - 1) {
-            const int j = __ffsll((long long)f) - 1;
-            if (pos < P.C) {
-                c_ab[pos] = (uint32_t)i | ((uint32_t)j << 8);
-                c_imp[pos] = make_float2(0.0f, 0.0f);
-                set_bit64(adj_lo, adj_hi, i, j);
-                set_bit64(adj_lo, adj_hi, j, i);
-            } else {
-                overflow = true;
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            for (unsigned f = w ? fresh[s].y : fresh[s].x; f; f &= f - 1) {
+                const int j = w * 32 + __ffs((int)f) - 1;
+                if (pos < P.C) {
+                    c_ab[pos] = (uint32_t)i | ((uint32_t)j << 8);
+                    c_imp[pos] = make_float2(0.0f, 0.0f);
+                    or_bit(adj, i, j);
+                    or_bit(adj, j, i);
+                } else {
+                    overflow = true;
+                }
+                ++pos;
             }
-            ++pos;
         }
         base += total;
     }
@@ -286,31 +325,36 @@ __device__ int find_new_contacts(const Grp<G>& g, const EnvS& S, const SimConst&
 // observation pass for the agents a lane owns (Flock.get_obs, mvmnt.py:181-222)
 // ------------------------------------------------------------------------------------------
 template <int G, int APL>
-__device__ void flock_observe(const Grp<G>& g, const EnvS& S, const SimConst& P, int env, const float* ang)
+__device__ void flock_observe(const Grp<G>& g, const EnvS<G * APL>& S, const SimConst& P, int env, const float* ang)
 {
-    constexpr int NC = G * APL;
-    const float* px = S.px<NC>(); const float* py = S.py<NC>();
+    const float2* pos = S.pos();
     const int N = P.N;
-    float ox[APL], oy[APL], best[APL];
+    float2 o[APL];
+    float best[APL];
     int bi[APL];
 #pragma unroll
     for (int s = 0; s < APL; ++s) {
-        const int i = g.gl + s * G;
-        ox[s] = px[i]; oy[s] = py[i];
+        o[s] = pos[g.gl + s * G];
         best[s] = __int_as_float(0x7f800000);
         bi[s] = -1;
     }
-    // nearest other agent: strict '<' over ascending j keeps the lowest index on ties (mvmnt.py:194)
-#pragma unroll 4
-    for (int j = 0; j < N; ++j) {
-        const float qx = px[j], qy = py[j];
+    // nearest other agent: strict '<' over ascending j keeps the lowest index on ties (mvmnt.py:194).
+    // Slot s only has to skip itself while j runs through its own 32-block.
 #pragma unroll
-        for (int s = 0; s < APL; ++s) {
-            const float dx = qx - ox[s], dy = qy - oy[s];
-            const float d2 = dx * dx + dy * dy;  // b2DistanceSquared, no FMA
-            const bool take = (d2 < best[s]) && (j != g.gl + s * G);
-            best[s] = take ? d2 : best[s];
-            bi[s] = take ? j : bi[s];
+    for (int jb = 0; jb < G * APL; jb += G) {
+        const int jend = (N - jb) < G ? (N - jb) : G;
+#pragma unroll 8
+        for (int jj = 0; jj < jend; ++jj) {
+            const float2 q = pos[jb + jj];
+            const bool notme = jj != g.gl;
+#pragma unroll
+            for (int s = 0; s < APL; ++s) {
+                const float dx = q.x - o[s].x, dy = q.y - o[s].y;
+                const float d2 = dx * dx + dy * dy;  // b2DistanceSquared, no FMA
+                const bool take = (s * G == jb) ? ((d2 < best[s]) && notme) : (d2 < best[s]);
+                best[s] = take ? d2 : best[s];
+                bi[s] = take ? (jb + jj) : bi[s];
+            }
         }
     }
 #pragma unroll
@@ -320,11 +364,12 @@ __device__ void flock_observe(const Grp<G>& g, const EnvS& S, const SimConst& P,
         const size_t gi = (size_t)env * N + i;
         float nn_d = __int_as_float(0x7f800000), nn_t = 0.0f;
         if (bi[s] >= 0) {
+            const float2 q = pos[bi[s]];
             nn_d = sqrtf(best[s]);
-            nn_t = wrap_pi_f(atan2f(py[bi[s]] - oy[s], px[bi[s]] - ox[s]) - ang[s]);
+            nn_t = wrap_pi_f(atan2f(q.y - o[s].y, q.x - o[s].x) - ang[s]);
         }
         const float2 tg = P.targets[(size_t)env * P.T + P.target_idx[i]];
-        const float tdx = tg.x - ox[s], tdy = tg.y - oy[s];
+        const float tdx = tg.x - o[s].x, tdy = tg.y - o[s].y;
         const float tg_r = sqrtf(tdx * tdx + tdy * tdy);
         const float tg_t = wrap_pi_f(atan2f(tdy, tdx) - ang[s]);
         P.nn_idx[gi] = bi[s];
@@ -334,10 +379,52 @@ __device__ void flock_observe(const Grp<G>& g, const EnvS& S, const SimConst& P,
             float sn, cn, st, ct;
             sincosf(nn_t, &sn, &cn);
             sincosf(tg_t, &st, &ct);
-            float2* o = reinterpret_cast<float2*>(P.obs) + gi * 3;
-            o[0] = make_float2(nn_d, cn);
-            o[1] = make_float2(sn, tg_r);
-            o[2] = make_float2(ct, st);
+            float2* ob = reinterpret_cast<float2*>(P.obs) + gi * 3;
+            ob[0] = make_float2(nn_d, cn);
+            ob[1] = make_float2(sn, tg_r);
+            ob[2] = make_float2(ct, st);
+        }
+    }
+}
+
+// TDM.get_obs (combat.py:206-227): for every alive agent i, every other alive agent j:
+// [r, theta, phi] and the ally flag.  Row i of the [N,N,4] output is written by the whole group
+// (lane <-> j) so that the 16-byte stores of a row are contiguous.
+template <int G, int APL>
+__device__ void tdm_observe(const Grp<G>& g, const EnvS<G * APL>& S, const SimConst& P, int env, uint2 alive)
+{
+    const float2* pos = S.pos();
+    const float* angs = S.ang();
+    const int N = P.N;
+    float2 o[APL];
+    float oa[APL];
+    int team[APL];
+#pragma unroll
+    for (int s = 0; s < APL; ++s) {
+        const int j = g.gl + s * G;
+        o[s] = pos[j];
+        oa[s] = angs[j];
+        team[s] = j < N ? P.team[j] : 0;
+    }
+    float4* out = reinterpret_cast<float4*>(P.obs) + (size_t)env * N * N;
+    for (int i = 0; i < N; ++i) {
+        const float2 p = pos[i];
+        const float a = angs[i];
+        const bool ai = bit_of(alive, i);
+        const int ti = P.team[i];
+#pragma unroll
+        for (int s = 0; s < APL; ++s) {
+            const int j = g.gl + s * G;
+            if (j >= N) continue;
+            float4 v = make_float4(0.0f, 0.0f, 0.0f, -1.0f);
+            if (ai && j != i && bit_of(alive, j)) {
+                const float dx = o[s].x - p.x, dy = o[s].y - p.y;
+                v.x = sqrtf(dx * dx + dy * dy);
+                v.y = wrap_pi_f(atan2f(dy, dx) - a);
+                v.z = wrap_pi_f(oa[s] - a);
+                v.w = (team[s] == ti) ? 1.0f : 0.0f;
+            }
+            out[(size_t)i * N + j] = v;
         }
     }
 }
@@ -345,68 +432,82 @@ __device__ void flock_observe(const Grp<G>& g, const EnvS& S, const SimConst& P,
 // ------------------------------------------------------------------------------------------
 // the step kernel
 // ------------------------------------------------------------------------------------------
-template <int G, int APL>
-__global__ void __launch_bounds__(128) macm_flock_step_kernel(const __grid_constant__ SimConst P,
-                                                              const void* __restrict__ actions)
+template <int G, int APL, int KIND>
+__global__ void __launch_bounds__(128) macm_step_kernel(const __grid_constant__ SimConst P,
+                                                        const void* __restrict__ actions)
 {
     constexpr int NC = G * APL;
     constexpr int GPW = 32 / G;
+    constexpr bool TDM = KIND == MACM_ENV_TDM;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Grp<G> g;
-    const int warp = threadIdx.x >> 5;
-    const int gidx = (threadIdx.x & 31) / G;
-    const int slot_in_block = warp * GPW + gidx;
+    const int slot_in_block = (threadIdx.x >> 5) * GPW + (threadIdx.x & 31) / G;
     const int env = blockIdx.x * (blockDim.x / 32) * GPW + slot_in_block;
     if (env >= P.E) return;  // whole group leaves together
     const int N = P.N;
-    EnvS S;
+    EnvS<NC> S;
     S.TC = P.TC;
     S.base = smem_raw + (size_t)slot_in_block * Lay<NC>::bytes(P.TC);
 
-    float* px = S.px<NC>(); float* py = S.py<NC>(); float* vx = S.vx<NC>(); float* vy = S.vy<NC>();
-    float* flx = S.flx<NC>(); float* fly = S.fly<NC>(); float* fhx = S.fhx<NC>(); float* fhy = S.fhy<NC>();
-    uint32_t* adj_lo = S.adj_lo<NC>(); uint32_t* adj_hi = S.adj_hi<NC>();
-    uint8_t* label = S.label<NC>();
-    uint32_t* misc = S.misc<NC>();
+    float2* pos = S.pos(); float2* vel = S.vel(); float4* fat = S.fat();
+    uint2* adj = S.adj();
+    uint8_t* label = S.label();
+    uint32_t* misc = S.misc();
 
     uint32_t* c_ab = P.c_ab + (size_t)env * P.C;
     float2* c_imp = P.c_imp + (size_t)env * P.C;
 
     // ---- phase 0: load state ---------------------------------------------------------------
-    float cx[APL], cy[APL], wx[APL], wy[APL], ang[APL], slp[APL], Fx[APL], Fy[APL];
+    float2 c[APL], v[APL], F[APL];
+    float ang[APL], slp[APL];
     float4 fatr[APL];
     bool valid[APL];
-    uint64_t alive = 0;
+    uint2 alive = make_uint2(0u, 0u);   // bodies that are active (have a proxy) during this step
     const int4 es = P.env_state[env];
     int cnt = P.c_cnt[env];
+    // TDM per-agent host state (combat.Agent): health, cool-downs (steps left), alive, hits taken
+    float health[APL];
+    int cd_atk[APL], cd_mov[APL], hits[APL];
+    bool was_alive[APL];
+    int team[APL];
 #pragma unroll
     for (int s = 0; s < APL; ++s) {
         const int i = g.gl + s * G;
         valid[s] = i < N;
+        team[s] = (TDM && valid[s]) ? P.team[i] : 0;
         const size_t gi = (size_t)env * N + (valid[s] ? i : 0);
         const float4 pv = P.posvel[gi];
         const float2 as = P.angsleep[gi];
         fatr[s] = P.fat[gi];
-        cx[s] = pv.x; cy[s] = pv.y; wx[s] = pv.z; wy[s] = pv.w; ang[s] = as.x; slp[s] = as.y;
-        if (!valid[s]) {  // padding agents: parked far away, never alive
-            cx[s] = cy[s] = 3.0e30f; wx[s] = wy[s] = 0.0f;
+        c[s] = make_float2(pv.x, pv.y); v[s] = make_float2(pv.z, pv.w); ang[s] = as.x; slp[s] = as.y;
+        was_alive[s] = valid[s];
+        if (TDM) {
+            const float4 td = P.tdm[gi];
+            health[s] = td.x; cd_atk[s] = __float_as_int(td.y); cd_mov[s] = __float_as_int(td.z);
+            const int w = __float_as_int(td.w);
+            was_alive[s] = valid[s] && (w & 1);
+            hits[s] = w >> 8;
+        }
+        if (!valid[s]) {  // padding agents: parked far away
+            c[s] = make_float2(3.0e30f, 3.0e30f); v[s] = make_float2(0.0f, 0.0f);
             fatr[s] = make_float4(3.0e30f, 3.0e30f, 3.0e30f, 3.0e30f);
         }
-        px[i] = cx[s]; py[i] = cy[s];
-        flx[i] = fatr[s].x; fly[i] = fatr[s].y; fhx[i] = fatr[s].z; fhy[i] = fatr[s].w;
-        adj_lo[i] = 0; adj_hi[i] = 0;
-        alive |= (uint64_t)g.ballot(valid[s]) << (s * G);
+        pos[i] = c[s];
+        fat[i] = fatr[s];
+        adj[i] = make_uint2(0u, 0u);
     }
-    if (g.gl == 0) { misc[0] = 0; misc[1] = 0; misc[2] = 0; }
+    if (g.gl == 0) { misc[0] = 0; misc[1] = 0; misc[2] = 0; misc[3] = 0; }
 
-    // ---- phase 1: actions -> angle, force (mvmnt.py:97-129), float64 like the reference -----
+    // ---- phase 1: actions -> angle, force (mvmnt.py:97-129 / combat.py:121-155), float64 like the reference
+    bool attack[APL];
 #pragma unroll
     for (int s = 0; s < APL; ++s) {
         const int i = g.gl + s * G;
-        Fx[s] = 0.0f; Fy[s] = 0.0f;
-        if (!valid[s]) continue;
+        F[s] = make_float2(0.0f, 0.0f);
+        attack[s] = false;
+        if (!was_alive[s]) continue;
         const size_t gi = (size_t)env * N + i;
-        if (P.action_mode == MACM_ACTION_DISCRETE) {
+        if (TDM || P.action_mode == MACM_ACTION_DISCRETE) {
             const uint32_t act = reinterpret_cast<const uint32_t*>(actions)[gi];
             const int a0 = (int)(act & 0xff) - 1, a1 = (int)((act >> 8) & 0xff) - 1, a2 = (int)((act >> 16) & 0xff) - 1;
             // body.angle = body.angle + (a2-1) * rotation_speed * (1/hz)   -> SetTransform rounds to fp32
@@ -417,13 +518,38 @@ __global__ void __launch_bounds__(128) macm_flock_step_kernel(const __grid_const
                 af = (float)(a - sg * (2 * NP_PI));
             }
             ang[s] = af;
-            const double A = (double)af;
-            double s1, c1, s2, c2;
-            sincos(A, &s1, &c1);
-            sincos(A + NP_PI / 2, &s2, &c2);
-            const double c = (a0 != 0 && a1 != 0) ? P.diag : 1.0;
-            Fx[s] = (float)((c1 * (double)a0 + c2 * (double)a1) * c * P.force);
-            Fy[s] = (float)((s1 * (double)a0 + s2 * (double)a1) * c * P.force);
+            // np.cos(angle), np.sin(angle), np.cos(angle + np.pi/2), np.sin(angle + np.pi/2) in float64.
+            // t = fl(A + pi/2) = (A + pi/2) + d exactly, with d from the rounding error of the sum and
+            // the tail of pi/2, so cos t = -sin(A + d) = -(sin A + d cos A), sin t = cos A - d sin A.
+            double s1, c1;
+            sincos_f32arg(P.sincos_tab, af, s1, c1);
+            const double A = (double)af, H = NP_PI / 2;
+            const double t = A + H, bb = t - A;
+            const double err = (A - (t - bb)) + (H - bb);          // A + H == t + err exactly (TwoSum)
+            const double d = -(err + 6.123233995736766e-17);       // pi/2 = H + 6.1232...e-17
+            const double c2 = -fma(d, c1, s1), s2 = fma(-d, s1, c1);
+            const double cc = (a0 != 0 && a1 != 0) ? P.diag : 1.0;
+            double force = P.force;
+            if (TDM) force = cd_mov[s] > 0 ? P.force_pen : P.force;   // Agent.force (combat.py:46-49)
+            F[s].x = (float)((c1 * (double)a0 + c2 * (double)a1) * cc * force);
+            F[s].y = (float)((s1 * (double)a0 + s2 * (double)a1) * cc * force);
+            if (TDM) {
+                // attack (combat.py:142-155): ray from the centre, melee_range along the heading
+                bool started = false;
+                if (cd_atk[s] <= 0) {
+                    if ((act >> 24) & 0xff) {
+                        attack[s] = true;
+                        started = true;
+                        cd_atk[s] = P.cd_atk_steps;
+                        cd_mov[s] = P.cd_mov_steps;
+                        const float dx = (float)(P.melee_range * c1), dy = (float)(P.melee_range * s1);
+                        reinterpret_cast<float4*>(S.nw())[i] = make_float4(c[s].x, c[s].y, c[s].x + dx, c[s].y + dy);
+                    }
+                } else {
+                    cd_atk[s] -= 1;
+                }
+                if ((P.flags & MACM_FLAG_REPAIR_MOV_COOLDOWN) && !started && cd_mov[s] > 0) cd_mov[s] -= 1;
+            }
         } else {
             const float2 ac = reinterpret_cast<const float2*>(actions)[gi];
             double x = (double)ac.x, y = (double)ac.y;
@@ -431,11 +557,80 @@ __global__ void __launch_bounds__(128) macm_flock_step_kernel(const __grid_const
                 x = sqrt(x * x / (x * x + y * y));
                 y = sqrt(y * y / (x * x + y * y));
             }
-            Fx[s] = (float)(x * P.force);
-            Fy[s] = (float)(y * P.force);
+            F[s].x = (float)(x * P.force);
+            F[s].y = (float)(y * P.force);
         }
     }
     g.sync();
+
+    // ---- phase 1b (TDM): closest-hit ray casts, health, deaths (combat.py:141-165, cm_framework.py:56-86)
+    bool now_alive[APL];
+#pragma unroll
+    for (int s = 0; s < APL; ++s) now_alive[s] = was_alive[s];
+    if (TDM) {
+        unsigned am[APL];
+        bool any_attack = false;
+#pragma unroll
+        for (int s = 0; s < APL; ++s) { am[s] = g.ballot(attack[s]); any_attack |= am[s] != 0u; }
+        if (any_attack) {
+            const float4* ray = reinterpret_cast<const float4*>(S.nw());
+#pragma unroll
+            for (int w = 0; w < APL; ++w) {
+                for (unsigned mm = am[w]; mm; mm &= mm - 1) {
+                    const int m = w * G + __ffs((int)mm) - 1;
+                    const float4 r4 = ray[m];
+                    // b2CircleShape::RayCast against every proxy; keep the smallest fraction,
+                    // lowest index among equal fractions
+                    unsigned fk[APL];
+                    unsigned key = 0xffffffffu;
+#pragma unroll
+                    for (int s = 0; s < APL; ++s) {
+                        fk[s] = 0xffffffffu;
+                        if (!was_alive[s]) continue;
+                        const float sx = r4.x - c[s].x, sy = r4.y - c[s].y;
+                        const float bq = (sx * sx + sy * sy) - P.radius * P.radius;
+                        const float rx = r4.z - r4.x, ry = r4.w - r4.y;
+                        const float cq = sx * rx + sy * ry;
+                        const float rr = rx * rx + ry * ry;
+                        const float sigma = cq * cq - rr * bq;
+                        if (sigma < 0.0f || rr < B2_EPSILON) continue;
+                        float a = -(cq + sqrtf(sigma));
+                        if (0.0f <= a && a <= 1.0f * rr) {
+                            a /= rr;
+                            fk[s] = __float_as_uint(a);   // a >= 0: bit order == value order
+                            key = min(key, fk[s]);
+                        }
+                    }
+                    const unsigned kmin = g.reduce_min(key);
+                    if (kmin != 0xffffffffu) {
+                        // lowest agent index with that fraction
+                        unsigned mine = 0xffffffffu;
+#pragma unroll
+                        for (int s = APL - 1; s >= 0; --s)
+                            if (fk[s] == kmin) mine = g.gl + s * G;
+                        const unsigned victim = g.reduce_min(mine);
+#pragma unroll
+                        for (int s = 0; s < APL; ++s) if ((unsigned)(g.gl + s * G) == victim) hits[s] += 1;
+                    }
+                }
+            }
+        }
+        // health -= melee_dmg per hit, in the reference's float64 (combat.py:153); deaths (combat.py:157-165)
+#pragma unroll
+        for (int s = 0; s < APL; ++s) {
+            if (!was_alive[s]) continue;
+            double h = (double)P.init_health;
+            for (int k = 0; k < hits[s]; ++k) h -= P.melee_dmg_d;
+            health[s] = (float)h;
+            if (h <= 0) now_alive[s] = false;   // body.active = False: proxy and contacts go at once
+        }
+        g.sync();
+    }
+#pragma unroll
+    for (int s = 0; s < APL; ++s) {
+        const unsigned bm = g.ballot(now_alive[s]);
+        if (s == 0) alive.x = bm; else alive.y = bm;
+    }
 
     bool overflow_c = false, overflow_t = false;
 
@@ -445,25 +640,25 @@ __global__ void __launch_bounds__(128) macm_flock_step_kernel(const __grid_const
             const int k = base + g.gl;
             if (k < cnt) {
                 const uint32_t ab = c_ab[k];
-                set_bit64(adj_lo, adj_hi, ab & 0xff, (ab >> 8) & 0xff);
-                set_bit64(adj_lo, adj_hi, (ab >> 8) & 0xff, ab & 0xff);
+                or_bit(adj, ab & 0xff, (ab >> 8) & 0xff);
+                or_bit(adj, (ab >> 8) & 0xff, ab & 0xff);
             }
         }
         g.sync();
         cnt = find_new_contacts<G, APL>(g, S, P, alive, alive, cnt, c_ab, c_imp, overflow_c);
 #pragma unroll
-        for (int s = 0; s < APL; ++s) { adj_lo[g.gl + s * G] = 0; adj_hi[g.gl + s * G] = 0; }
+        for (int s = 0; s < APL; ++s) adj[g.gl + s * G] = make_uint2(0u, 0u);
         g.sync();
     }
 
     // ---- phase 2: b2ContactManager::Collide --------------------------------------------------
-    // destroy contacts whose fat AABBs stopped overlapping, narrowphase the rest, compact in
-    // place (birth order is preserved), stage the touching ones for the solver
+    // destroy contacts whose fat AABBs stopped overlapping (or whose body was deactivated),
+    // narrowphase the rest, compact in place (birth order is preserved), stage the touching ones
     int tc = 0;
     {
-        uint8_t* t_a = S.t_a<NC>(); uint8_t* t_b = S.t_b<NC>();
-        float* t_nI = S.t_nI<NC>(); float* t_tI = S.t_tI<NC>();
-        uint16_t* t_slot = S.t_slot<NC>();
+        float2* t_imp = S.t_imp();
+        uint32_t* t_ew = S.t_ew();
+        uint16_t* t_slot = S.t_slot();
         int w = 0;
         bool dup = false;
         for (int base = 0; base < cnt; base += G) {
@@ -474,32 +669,33 @@ __global__ void __launch_bounds__(128) macm_flock_step_kernel(const __grid_const
             if (in) { ab = c_ab[k]; imp = c_imp[k]; }
             g.sync();  // every lane holds its record before any lane compacts over it
             const int a = ab & 0xff, b = (ab >> 8) & 0xff;
-            const bool keep = in && aabb_overlap(flx[a], fly[a], fhx[a], fhy[a], flx[b], fly[b], fhx[b], fhy[b]);
+            bool keep = in && aabb_overlap(fat[a], fat[b]);
+            if (TDM) keep = keep && bit_of(alive, a) && bit_of(alive, b);
             bool touch = false;
             if (keep) {
-                const float dx = px[b] - px[a], dy = py[b] - py[a];
+                const float2 pa = pos[a], pb = pos[b];
+                const float dx = pb.x - pa.x, dy = pb.y - pa.y;
                 touch = !((dx * dx + dy * dy) > P.rsum2);
             }
             const unsigned km = g.ballot(keep), tm = g.ballot(touch);
             if (keep) {
-                const int pos = w + __popc(km & g.below());
+                const int p = w + __popc(km & g.below());
                 const bool was = (ab >> 16) & 1;
                 const float nI = (touch && was) ? imp.x : 0.0f, tI = (touch && was) ? imp.y : 0.0f;
-                c_ab[pos] = (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)touch << 16);
+                c_ab[p] = (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)touch << 16);
                 const int tp = tc + __popc(tm & g.below());
                 // touching contacts get their impulses from StoreImpulses after the solver
-                if (!touch || tp >= P.TC) c_imp[pos] = make_float2(nI, tI);
-                set_bit64(adj_lo, adj_hi, a, b);
-                set_bit64(adj_lo, adj_hi, b, a);
-                if (touch) {
-                    if (tp < P.TC) {
-                        t_a[tp] = (uint8_t)a; t_b[tp] = (uint8_t)b; t_nI[tp] = nI; t_tI[tp] = tI;
-                        t_slot[tp] = (uint16_t)pos;
-                        // does any body carry two touching contacts?
-                        const uint32_t oa = atomicOr(&misc[a >> 5], 1u << (a & 31));
-                        const uint32_t ob = atomicOr(&misc[b >> 5], 1u << (b & 31));
-                        dup |= ((oa >> (a & 31)) & 1) | ((ob >> (b & 31)) & 1);
-                    }
+                if (!touch || tp >= P.TC) c_imp[p] = make_float2(nI, tI);
+                or_bit(adj, a, b);
+                or_bit(adj, b, a);
+                if (touch && tp < P.TC) {
+                    t_ew[tp] = (uint32_t)a | ((uint32_t)b << 6);
+                    t_imp[tp] = make_float2(nI, tI);
+                    t_slot[tp] = (uint16_t)p;
+                    // bodies with a touching contact (misc[0..1]); does any body carry two?
+                    const uint32_t oa = atomicOr(&misc[a >> 5], 1u << (a & 31));
+                    const uint32_t ob = atomicOr(&misc[b >> 5], 1u << (b & 31));
+                    dup |= ((oa >> (a & 31)) & 1) | ((ob >> (b & 31)) & 1);
                 }
             }
             w += __popc(km);
@@ -514,17 +710,19 @@ __global__ void __launch_bounds__(128) macm_flock_step_kernel(const __grid_const
 #pragma unroll
     for (int s = 0; s < APL; ++s) {
         const int i = g.gl + s * G;
-        // v += h * (gravityScale * gravity + invMass * force); v *= damping
-        wx[s] += P.h * (P.inv_mass * Fx[s]);
-        wy[s] += P.h * (P.inv_mass * Fy[s]);
-        wx[s] *= P.damp;
-        wy[s] *= P.damp;
-        vx[i] = wx[s]; vy[i] = wy[s];
+        if (now_alive[s]) {
+            // v += h * (gravityScale * gravity + invMass * force); v *= damping
+            v[s].x += P.h * (P.inv_mass * F[s].x);
+            v[s].y += P.h * (P.inv_mass * F[s].y);
+            v[s].x *= P.damp;
+            v[s].y *= P.damp;
+        }
+        vel[i] = v[s];
         label[i] = (uint8_t)i;
-        S.isl_act<NC>()[i] = 1;
-        S.isl_bad<NC>()[i] = 0;
-        S.lastlvl<NC>()[i] = 0;
-        S.head<NC>()[i] = 0xff;
+        S.isl_act()[i] = 1;
+        S.isl_bad()[i] = 0;
+        S.lastlvl()[i] = 0;
+        S.head()[i] = EW_NONE;
     }
     g.sync();
 
@@ -536,57 +734,54 @@ __global__ void __launch_bounds__(128) macm_flock_step_kernel(const __grid_const
     int nlev = tc > 0 ? 1 : 0;
     const bool multi = misc[2] != 0;
     if (tc > 0) {
-        uint8_t* t_a = S.t_a<NC>(); uint8_t* t_b = S.t_b<NC>();
-        uint16_t* ord = S.ord<NC>(); uint8_t* lvl = S.lvl<NC>();
+        uint32_t* t_ew = S.t_ew();
+        uint16_t* ordlvl = S.ordlvl();
         if (!multi) {
             // every body has at most one touching contact: contacts are independent, any order
             // gives the same bits; islands are the pairs themselves (seed = higher index)
             for (int k = g.gl; k < tc; k += G) {
-                ord[k] = (uint16_t)k;
-                lvl[k] = 1;
-                const int a = t_a[k], b = t_b[k];
-                label[a] = (uint8_t)b;
-                label[b] = (uint8_t)b;
+                ordlvl[k] = (uint16_t)(k | (1 << 8));
+                const uint32_t ew = t_ew[k];
+                label[EW_A(ew)] = (uint8_t)EW_B(ew);
+                label[EW_B(ew)] = (uint8_t)EW_B(ew);
             }
         } else {
             int L = 1;
             if (g.gl == 0) {
-                uint8_t* stack = S.stack<NC>(); uint8_t* head = S.head<NC>(); uint8_t* lastlvl = S.lastlvl<NC>();
-                uint8_t* nxt_a = S.nxt_a<NC>(); uint8_t* nxt_b = S.nxt_b<NC>(); uint8_t* taken = S.taken<NC>();
+                uint8_t* stack = S.stack(); uint8_t* head = S.head(); uint8_t* lastlvl = S.lastlvl();
                 for (int t = 0; t < tc; ++t) {
-                    const int a = t_a[t], b = t_b[t];
-                    nxt_a[t] = head[a]; head[a] = (uint8_t)t;
-                    nxt_b[t] = head[b]; head[b] = (uint8_t)t;
-                    taken[t] = 0;
+                    const uint32_t ew = t_ew[t];
+                    const int a = EW_A(ew), b = EW_B(ew);
+                    t_ew[t] = ew | ((uint32_t)head[a] << 12) | ((uint32_t)head[b] << 20);
+                    head[a] = (uint8_t)t;
+                    head[b] = (uint8_t)t;
                 }
                 // bodies with a touching contact that are not in an island yet
-                uint64_t rem = (uint64_t)misc[0] | ((uint64_t)misc[1] << 32);
+                uint32_t rem_lo = misc[0], rem_hi = misc[1];
                 int nord = 0;
-                while (rem) {
-                    const int seed = 63 - __clzll((long long)rem);
+                while (rem_lo | rem_hi) {
+                    const int seed = rem_hi ? (63 - __clz((int)rem_hi)) : (31 - __clz((int)rem_lo));
                     int sp = 0;
                     stack[sp++] = (uint8_t)seed;
-                    rem &= ~(1ull << seed);
+                    if (seed < 32) rem_lo &= ~(1u << seed); else rem_hi &= ~(1u << (seed - 32));
                     while (sp > 0) {
                         const int b = stack[--sp];
                         label[b] = (uint8_t)seed;
-                        for (int t = head[b]; t != 0xff;) {
-                            const int ta = t_a[t], tb = t_b[t];
-                            const int nx = (ta == b) ? nxt_a[t] : nxt_b[t];
-                            if (!taken[t]) {
-                                taken[t] = 1;
-                                ord[nord] = (uint16_t)t;
+                        for (int t = head[b]; t != EW_NONE;) {
+                            const uint32_t ew = t_ew[t];
+                            const int ta = EW_A(ew), tb = EW_B(ew);
+                            const int nx = (ta == b) ? EW_NA(ew) : EW_NB(ew);
+                            if (!(ew & EW_TAKEN)) {
+                                t_ew[t] = ew | EW_TAKEN;
                                 const int l = 1 + max((int)lastlvl[ta], (int)lastlvl[tb]);
-                                lvl[nord] = (uint8_t)l;
+                                ordlvl[nord++] = (uint16_t)(t | (l << 8));
                                 lastlvl[ta] = (uint8_t)l;
                                 lastlvl[tb] = (uint8_t)l;
                                 L = max(L, l);
-                                ++nord;
                                 const int other = (ta == b) ? tb : ta;
-                                if ((rem >> other) & 1) {
-                                    rem &= ~(1ull << other);
-                                    stack[sp++] = (uint8_t)other;
-                                }
+                                const uint32_t ob = 1u << (other & 31);
+                                if (other < 32) { if (rem_lo & ob) { rem_lo &= ~ob; stack[sp++] = (uint8_t)other; } }
+                                else { if (rem_hi & ob) { rem_hi &= ~ob; stack[sp++] = (uint8_t)other; } }
                             }
                             t = nx;
                         }
@@ -605,156 +800,153 @@ __global__ void __launch_bounds__(128) macm_flock_step_kernel(const __grid_const
     int ka = 0, kb = 0, klv = 0, kt = 0, kisl = 0;
     float knx = 1.0f, kny = 0.0f, knI = 0.0f, ktI = 0.0f;
     if (tc > 0) {
-        uint8_t* t_a = S.t_a<NC>(); uint8_t* t_b = S.t_b<NC>();
-        float* t_nx = S.t_nx<NC>(); float* t_ny = S.t_ny<NC>();
-        float* t_nI = S.t_nI<NC>(); float* t_tI = S.t_tI<NC>();
-        uint16_t* ord = S.ord<NC>(); uint8_t* lvl = S.lvl<NC>();
+        float2* t_n = S.t_n(); float2* t_imp = S.t_imp();
+        const uint32_t* t_ew = S.t_ew();
+        const uint16_t* ordlvl = S.ordlvl();
         const float mass_n = P.normal_mass, mass_t = P.normal_mass;
         // b2ContactSolver ctor + InitializeVelocityConstraints: world manifold at the
         // pre-integration positions, impulses scaled by dtRatio
         const float ratio = (es.x == 0) ? 0.0f : P.dt_ratio;  // inv_dt0 == 0 on a world's first step
         for (int k = g.gl; k < tc; k += G) {
-            const int t = ord[k];
-            const int a = t_a[t], b = t_b[t];
+            const int ol = ordlvl[k];
+            const int t = ol & 0xff;
+            const uint32_t ew = t_ew[t];
+            const int a = EW_A(ew), b = EW_B(ew);
+            const float2 pa = pos[a], pb = pos[b];
             float nx = 1.0f, ny = 0.0f;
-            const float dx = px[b] - px[a], dy = py[b] - py[a];
+            const float dx = pb.x - pa.x, dy = pb.y - pa.y;
             // b2DistanceSquared(pointA, pointB) is (A - B).(A - B); squares are sign-blind
             if ((dx * dx + dy * dy) > B2_EPSILON * B2_EPSILON) { nx = dx; ny = dy; b2normalize(nx, ny); }
-            float nI = 0.0f, tI = 0.0f;
-            if (P.warm_starting) { nI = ratio * t_nI[t]; tI = ratio * t_tI[t]; }
+            float2 im = make_float2(0.0f, 0.0f);
+            if (P.warm_starting) { im = t_imp[t]; im.x = ratio * im.x; im.y = ratio * im.y; }
             if (k < G) {
-                kt = t; ka = a; kb = b; klv = lvl[k]; kisl = label[a];
-                knx = nx; kny = ny; knI = nI; ktI = tI;
+                kt = t; ka = a; kb = b; klv = ol >> 8; kisl = label[a];
+                knx = nx; kny = ny; knI = im.x; ktI = im.y;
             } else {
-                t_nx[t] = nx; t_ny[t] = ny; t_nI[t] = nI; t_tI[t] = tI;
+                t_n[t] = make_float2(nx, ny); t_imp[t] = im;
             }
         }
         if (nlev == 1) {
             // independent contacts: warm start + all iterations without leaving registers
             if (has) {
-                float vax = vx[ka], vay = vy[ka], vbx = vx[kb], vby = vy[kb];
-                {
-                    const float tx = kny, ty = -knx;
-                    const float Px = knI * knx + ktI * tx, Py = knI * kny + ktI * ty;
-                    vax -= P.inv_mass * Px; vay -= P.inv_mass * Py;
-                    vbx += P.inv_mass * Px; vby += P.inv_mass * Py;
-                }
+                float2 va = vel[ka], vb = vel[kb];
+                warm_start(knx, kny, knI, ktI, P.inv_mass, va, vb);
                 for (int it = 0; it < P.vel_iters; ++it)
-                    solve_velocity(knx, kny, P.friction, mass_n, mass_t, P.inv_mass, knI, ktI, vax, vay, vbx, vby);
-                vx[ka] = vax; vy[ka] = vay; vx[kb] = vbx; vy[kb] = vby;
+                    solve_velocity(knx, kny, P.friction, mass_n, mass_t, P.inv_mass, knI, ktI, va, vb);
+                vel[ka] = va; vel[kb] = vb;
             }
             for (int k = g.gl + G; k < tc; k += G) {
-                const int t = ord[k];
-                const int a = t_a[t], b = t_b[t];
-                const float nx = t_nx[t], ny = t_ny[t];
-                float nI = t_nI[t], tI = t_tI[t];
-                float vax = vx[a], vay = vy[a], vbx = vx[b], vby = vy[b];
-                {
-                    const float tx = ny, ty = -nx;
-                    const float Px = nI * nx + tI * tx, Py = nI * ny + tI * ty;
-                    vax -= P.inv_mass * Px; vay -= P.inv_mass * Py;
-                    vbx += P.inv_mass * Px; vby += P.inv_mass * Py;
-                }
+                const int t = ordlvl[k] & 0xff;
+                const uint32_t ew = t_ew[t];
+                const int a = EW_A(ew), b = EW_B(ew);
+                const float2 n = t_n[t];
+                float2 im = t_imp[t];
+                float2 va = vel[a], vb = vel[b];
+                warm_start(n.x, n.y, im.x, im.y, P.inv_mass, va, vb);
                 for (int it = 0; it < P.vel_iters; ++it)
-                    solve_velocity(nx, ny, P.friction, mass_n, mass_t, P.inv_mass, nI, tI, vax, vay, vbx, vby);
-                vx[a] = vax; vy[a] = vay; vx[b] = vbx; vy[b] = vby;
-                t_nI[t] = nI; t_tI[t] = tI;
+                    solve_velocity(n.x, n.y, P.friction, mass_n, mass_t, P.inv_mass, im.x, im.y, va, vb);
+                vel[a] = va; vel[b] = vb;
+                t_imp[t] = im;
             }
             g.sync();
         } else {
             // WarmStart, in order
             for (int lev = 1; lev <= nlev; ++lev) {
                 if (has && klv == lev) {
-                    const float tx = kny, ty = -knx;
-                    const float Px = knI * knx + ktI * tx, Py = knI * kny + ktI * ty;
-                    vx[ka] -= P.inv_mass * Px; vy[ka] -= P.inv_mass * Py;
-                    vx[kb] += P.inv_mass * Px; vy[kb] += P.inv_mass * Py;
+                    float2 va = vel[ka], vb = vel[kb];
+                    warm_start(knx, kny, knI, ktI, P.inv_mass, va, vb);
+                    vel[ka] = va; vel[kb] = vb;
                 }
                 for (int k = g.gl + G; k < tc; k += G) {
-                    if (lvl[k] != lev) continue;
-                    const int t = ord[k];
-                    const int a = t_a[t], b = t_b[t];
-                    const float nx = t_nx[t], ny = t_ny[t], nI = t_nI[t], tI = t_tI[t];
-                    const float tx = ny, ty = -nx;
-                    const float Px = nI * nx + tI * tx, Py = nI * ny + tI * ty;
-                    vx[a] -= P.inv_mass * Px; vy[a] -= P.inv_mass * Py;
-                    vx[b] += P.inv_mass * Px; vy[b] += P.inv_mass * Py;
+                    const int ol = ordlvl[k];
+                    if ((ol >> 8) != lev) continue;
+                    const int t = ol & 0xff;
+                    const uint32_t ew = t_ew[t];
+                    const int a = EW_A(ew), b = EW_B(ew);
+                    const float2 n = t_n[t], im = t_imp[t];
+                    float2 va = vel[a], vb = vel[b];
+                    warm_start(n.x, n.y, im.x, im.y, P.inv_mass, va, vb);
+                    vel[a] = va; vel[b] = vb;
                 }
                 g.sync();
             }
             for (int it = 0; it < P.vel_iters; ++it) {
                 for (int lev = 1; lev <= nlev; ++lev) {
                     if (has && klv == lev) {
-                        float vax = vx[ka], vay = vy[ka], vbx = vx[kb], vby = vy[kb];
-                        solve_velocity(knx, kny, P.friction, mass_n, mass_t, P.inv_mass, knI, ktI, vax, vay, vbx, vby);
-                        vx[ka] = vax; vy[ka] = vay; vx[kb] = vbx; vy[kb] = vby;
+                        float2 va = vel[ka], vb = vel[kb];
+                        solve_velocity(knx, kny, P.friction, mass_n, mass_t, P.inv_mass, knI, ktI, va, vb);
+                        vel[ka] = va; vel[kb] = vb;
                     }
                     for (int k = g.gl + G; k < tc; k += G) {
-                        if (lvl[k] != lev) continue;
-                        const int t = ord[k];
-                        const int a = t_a[t], b = t_b[t];
-                        float nI = t_nI[t], tI = t_tI[t];
-                        float vax = vx[a], vay = vy[a], vbx = vx[b], vby = vy[b];
-                        solve_velocity(t_nx[t], t_ny[t], P.friction, mass_n, mass_t, P.inv_mass, nI, tI, vax, vay,
-                                       vbx, vby);
-                        vx[a] = vax; vy[a] = vay; vx[b] = vbx; vy[b] = vby;
-                        t_nI[t] = nI; t_tI[t] = tI;
+                        const int ol = ordlvl[k];
+                        if ((ol >> 8) != lev) continue;
+                        const int t = ol & 0xff;
+                        const uint32_t ew = t_ew[t];
+                        const int a = EW_A(ew), b = EW_B(ew);
+                        const float2 n = t_n[t];
+                        float2 im = t_imp[t];
+                        float2 va = vel[a], vb = vel[b];
+                        solve_velocity(n.x, n.y, P.friction, mass_n, mass_t, P.inv_mass, im.x, im.y, va, vb);
+                        vel[a] = va; vel[b] = vb;
+                        t_imp[t] = im;
                     }
                     g.sync();
                 }
             }
         }
         // StoreImpulses -> manifold (next step's warm start)
-        uint16_t* t_slot = S.t_slot<NC>();
+        const uint16_t* t_slot = S.t_slot();
         if (has) c_imp[t_slot[kt]] = make_float2(knI, ktI);
-        for (int k = g.gl + G; k < tc; k += G) { const int t = ord[k]; c_imp[t_slot[t]] = make_float2(t_nI[t], t_tI[t]); }
+        for (int k = g.gl + G; k < tc; k += G) { const int t = ordlvl[k] & 0xff; c_imp[t_slot[t]] = t_imp[t]; }
     }
 
     // ---- phase 6: integrate positions ------------------------------------------------------------
-    float c0x[APL], c0y[APL];
+    float2 c0[APL];
 #pragma unroll
     for (int s = 0; s < APL; ++s) {
         const int i = g.gl + s * G;
-        c0x[s] = cx[s]; c0y[s] = cy[s];
-        float v_x = vx[i], v_y = vy[i];
-        const float trx = P.h * v_x, try_ = P.h * v_y;
+        c0[s] = c[s];
+        if (!now_alive[s]) continue;
+        float2 w = vel[i];
+        const float trx = P.h * w.x, try_ = P.h * w.y;
         if ((trx * trx + try_ * try_) > B2_MAX_TRANSLATION * B2_MAX_TRANSLATION) {
             const float ratio = B2_MAX_TRANSLATION / sqrtf(trx * trx + try_ * try_);
-            v_x *= ratio; v_y *= ratio;
+            w.x *= ratio; w.y *= ratio;
         }
-        cx[s] += P.h * v_x;
-        cy[s] += P.h * v_y;
-        wx[s] = v_x; wy[s] = v_y;
+        c[s].x += P.h * w.x;
+        c[s].y += P.h * w.y;
+        v[s] = w;
     }
     g.sync();
 #pragma unroll
-    for (int s = 0; s < APL; ++s) { px[g.gl + s * G] = cx[s]; py[g.gl + s * G] = cy[s]; }
+    for (int s = 0; s < APL; ++s) pos[g.gl + s * G] = c[s];
     g.sync();
 
     // ---- phase 7: contact solver, position part (per-island early exit) ---------------------------
     {
-        uint8_t* isl_act = S.isl_act<NC>(); uint8_t* isl_bad = S.isl_bad<NC>();
+        uint8_t* isl_act = S.isl_act(); uint8_t* isl_bad = S.isl_bad();
         if (tc > 0) {
-            uint8_t* t_a = S.t_a<NC>(); uint8_t* t_b = S.t_b<NC>();
-            uint16_t* ord = S.ord<NC>(); uint8_t* lvl = S.lvl<NC>();
+            const uint32_t* t_ew = S.t_ew();
+            const uint16_t* ordlvl = S.ordlvl();
             for (int it = 0; it < P.pos_iters; ++it) {
                 for (int lev = 1; lev <= nlev; ++lev) {
                     if (has && klv == lev && isl_act[kisl]) {
-                        float cax = px[ka], cay = py[ka], cbx = px[kb], cby = py[kb];
-                        const float sep = solve_position(P.radius, P.k_sum, P.inv_mass, cax, cay, cbx, cby);
-                        px[ka] = cax; py[ka] = cay; px[kb] = cbx; py[kb] = cby;
+                        float2 ca = pos[ka], cb = pos[kb];
+                        const float sep = solve_position(P.radius, P.k_sum, P.inv_mass, ca, cb);
+                        pos[ka] = ca; pos[kb] = cb;
                         // island not solved while min(0, separations) < -3 * linearSlop
                         if (!(b2min(0.0f, sep) >= -3.0f * B2_LINEAR_SLOP)) isl_bad[kisl] = 1;
                     }
                     for (int k = g.gl + G; k < tc; k += G) {
-                        if (lvl[k] != lev) continue;
-                        const int t = ord[k];
-                        const int a = t_a[t], b = t_b[t];
+                        const int ol = ordlvl[k];
+                        if ((ol >> 8) != lev) continue;
+                        const uint32_t ew = t_ew[ol & 0xff];
+                        const int a = EW_A(ew), b = EW_B(ew);
                         const int isl = label[a];
                         if (!isl_act[isl]) continue;
-                        float cax = px[a], cay = py[a], cbx = px[b], cby = py[b];
-                        const float sep = solve_position(P.radius, P.k_sum, P.inv_mass, cax, cay, cbx, cby);
-                        px[a] = cax; py[a] = cay; px[b] = cbx; py[b] = cby;
+                        float2 ca = pos[a], cb = pos[b];
+                        const float sep = solve_position(P.radius, P.k_sum, P.inv_mass, ca, cb);
+                        pos[a] = ca; pos[b] = cb;
                         if (!(b2min(0.0f, sep) >= -3.0f * B2_LINEAR_SLOP)) isl_bad[isl] = 1;
                     }
                     g.sync();
@@ -772,7 +964,7 @@ __global__ void __launch_bounds__(128) macm_flock_step_kernel(const __grid_const
                 if (!g.ballot(any_bad)) break;
             }
 #pragma unroll
-            for (int s = 0; s < APL; ++s) { cx[s] = px[g.gl + s * G]; cy[s] = py[g.gl + s * G]; }
+            for (int s = 0; s < APL; ++s) c[s] = pos[g.gl + s * G];
         } else if (P.pos_iters > 0) {
 #pragma unroll
             for (int s = 0; s < APL; ++s) isl_act[g.gl + s * G] = 0;
@@ -785,71 +977,89 @@ __global__ void __launch_bounds__(128) macm_flock_step_kernel(const __grid_const
         const float tol2 = B2_LINEAR_SLEEP_TOLERANCE * B2_LINEAR_SLEEP_TOLERANCE;
 #pragma unroll
         for (int s = 0; s < APL; ++s) {
-            if ((wx[s] * wx[s] + wy[s] * wy[s]) > tol2) slp[s] = 0.0f;
+            if (!now_alive[s]) continue;
+            if ((v[s].x * v[s].x + v[s].y * v[s].y) > tol2) slp[s] = 0.0f;
             else slp[s] += P.h;
-            cand |= valid[s] && slp[s] >= B2_TIME_TO_SLEEP;
+            cand |= slp[s] >= B2_TIME_TO_SLEEP;
         }
         if (g.ballot(cand)) {
-            uint32_t* isl_min = S.isl_min<NC>();
-            uint8_t* isl_act = S.isl_act<NC>();
+            uint32_t* isl_min = S.isl_min();
+            uint8_t* isl_act = S.isl_act();
 #pragma unroll
             for (int s = 0; s < APL; ++s) isl_min[g.gl + s * G] = 0x7f7fffffu;  // b2_maxFloat
             g.sync();
 #pragma unroll
             for (int s = 0; s < APL; ++s)
-                if (valid[s]) atomicMin(&isl_min[label[g.gl + s * G]], __float_as_uint(slp[s]));
+                if (now_alive[s]) atomicMin(&isl_min[label[g.gl + s * G]], __float_as_uint(slp[s]));
             g.sync();
 #pragma unroll
             for (int s = 0; s < APL; ++s) {
                 const int isl = label[g.gl + s * G];
                 const bool solved = (P.pos_iters > 0) && !isl_act[isl];
-                if (valid[s] && __uint_as_float(isl_min[isl]) >= B2_TIME_TO_SLEEP && solved) {
+                if (now_alive[s] && __uint_as_float(isl_min[isl]) >= B2_TIME_TO_SLEEP && solved) {
                     // SetAwake(false); the next ApplyForce(wake=True) wakes the body again
-                    slp[s] = 0.0f; wx[s] = 0.0f; wy[s] = 0.0f;
+                    slp[s] = 0.0f; v[s] = make_float2(0.0f, 0.0f);
                 }
             }
         }
     }
 
     // ---- phase 9: SynchronizeFixtures -> b2DynamicTree::MoveProxy -----------------------------------
-    uint64_t moved = 0;
+    uint2 moved = make_uint2(0u, 0u);
 #pragma unroll
     for (int s = 0; s < APL; ++s) {
         const int i = g.gl + s * G;
         const float r = P.radius;
-        const float lox = b2min(c0x[s] - r, cx[s] - r), loy = b2min(c0y[s] - r, cy[s] - r);
-        const float hix = b2max(c0x[s] + r, cx[s] + r), hiy = b2max(c0y[s] + r, cy[s] + r);
+        const float lox = b2min(c0[s].x - r, c[s].x - r), loy = b2min(c0[s].y - r, c[s].y - r);
+        const float hix = b2max(c0[s].x + r, c[s].x + r), hiy = b2max(c0[s].y + r, c[s].y + r);
         const bool contains = fatr[s].x <= lox && fatr[s].y <= loy && hix <= fatr[s].z && hiy <= fatr[s].w;
-        const bool mv = valid[s] && !contains;
+        const bool mv = now_alive[s] && !contains;
         if (mv) {
             float nlx = lox - B2_AABB_EXTENSION, nly = loy - B2_AABB_EXTENSION;
             float nhx = hix + B2_AABB_EXTENSION, nhy = hiy + B2_AABB_EXTENSION;
-            const float dx = B2_AABB_MULTIPLIER * (cx[s] - c0x[s]), dy = B2_AABB_MULTIPLIER * (cy[s] - c0y[s]);
+            const float dx = B2_AABB_MULTIPLIER * (c[s].x - c0[s].x), dy = B2_AABB_MULTIPLIER * (c[s].y - c0[s].y);
             if (dx < 0.0f) nlx += dx; else nhx += dx;
             if (dy < 0.0f) nly += dy; else nhy += dy;
             fatr[s] = make_float4(nlx, nly, nhx, nhy);
-            flx[i] = nlx; fly[i] = nly; fhx[i] = nhx; fhy[i] = nhy;
+            fat[i] = fatr[s];
         }
-        moved |= (uint64_t)g.ballot(mv) << (s * G);
+        const unsigned bm = g.ballot(mv);
+        if (s == 0) moved.x = bm; else moved.y = bm;
     }
     g.sync();
 
     // ---- phase 10: FindNewContacts ------------------------------------------------------------------
-    if (moved) cnt = find_new_contacts<G, APL>(g, S, P, moved, alive, cnt, c_ab, c_imp, overflow_c);
+    if (moved.x | moved.y) cnt = find_new_contacts<G, APL>(g, S, P, moved, alive, cnt, c_ab, c_imp, overflow_c);
 
     // ---- phase 11: rewards (mvmnt.py:160-179), time/done (mvmnt.py:134-136) ---------------------------
     const int step = es.x + 1;
-    const bool done = step >= P.done_step;
+    bool done = step >= P.done_step;
+    int winner = es.w;
+    if (TDM) {
+        // alive_teams (combat.py:172-182)
+        int teams_alive = 0, last = -1;
+        for (int t = 0; t < MACM_MAX_TEAMS; ++t) {
+            bool mine = false;
+#pragma unroll
+            for (int s = 0; s < APL; ++s) mine |= now_alive[s] && team[s] == t;
+            if (g.ballot(mine)) { ++teams_alive; last = t; }
+        }
+        if (teams_alive == 1) { done = true; winner = last; }
+        if (teams_alive == 0) done = true;
+    }
 #pragma unroll
     for (int s = 0; s < APL; ++s) {
         const int i = g.gl + s * G;
         if (!valid[s]) continue;
         const size_t gi = (size_t)env * N + i;
-        const bool col = (adj_lo[i] | adj_hi[i]) != 0;
+        const uint2 row = adj[i];
+        const bool col = (row.x | row.y) != 0;
         float rew = -1.0f;
-        if (!col) {
+        if (TDM) {
+            rew = (now_alive[s] && col) ? -1.0f : 0.0f;
+        } else if (!col) {
             const float2 tg = P.targets[(size_t)env * P.T + P.target_idx[i]];
-            const float dx = tg.x - cx[s], dy = tg.y - cy[s];
+            const float dx = tg.x - c[s].x, dy = tg.y - c[s].y;
             const float d2 = dx * dx + dy * dy;
             if (P.reward_mode == MACM_REWARD_LINEAR) rew = (-sqrtf(d2) / 35.0f) + 1.0f;
             else rew = (d2 < P.binary_thr) ? 1.0f : 0.0f;
@@ -857,9 +1067,14 @@ __global__ void __launch_bounds__(128) macm_flock_step_kernel(const __grid_const
         P.rewards[gi] = rew;
         P.collided[gi] = (uint8_t)col;
         // ---- phase 12: write state back ----
-        P.posvel[gi] = make_float4(cx[s], cy[s], wx[s], wy[s]);
+        P.posvel[gi] = make_float4(c[s].x, c[s].y, v[s].x, v[s].y);
         P.angsleep[gi] = make_float2(ang[s], slp[s]);
         P.fat[gi] = fatr[s];
+        if (TDM) {
+            P.tdm[gi] = make_float4(health[s], __int_as_float(cd_atk[s]), __int_as_float(cd_mov[s]),
+                                    __int_as_float((now_alive[s] ? 1 : 0) | (hits[s] << 8)));
+            S.ang()[i] = ang[s];
+        }
     }
     {
         const bool oc = g.ballot(overflow_c) != 0, ot = g.ballot(overflow_t) != 0;
@@ -868,17 +1083,22 @@ __global__ void __launch_bounds__(128) macm_flock_step_kernel(const __grid_const
                               (ot ? MACM_ENV_TOUCH_OVERFLOW : 0);
             P.c_cnt[env] = cnt;
             P.done[env] = (uint8_t)done;
-            P.env_state[env] = make_int4(step, flags, tc, es.w);
+            P.env_state[env] = make_int4(step, flags, tc, winner);
         }
     }
 
-    // ---- phase 13: observations (mvmnt.py:181-222) ------------------------------------------------
-    flock_observe<G, APL>(g, S, P, env, ang);
+    // ---- phase 13: observations (mvmnt.py:181-222 / combat.py:206-227) ----------------------------
+    if (TDM) {
+        g.sync();
+        tdm_observe<G, APL>(g, S, P, env, alive);
+    } else {
+        flock_observe<G, APL>(g, S, P, env, ang);
+    }
 }
 
 // get_obs() alone
-template <int G, int APL>
-__global__ void __launch_bounds__(128) macm_flock_observe_kernel(const __grid_constant__ SimConst P)
+template <int G, int APL, int KIND>
+__global__ void __launch_bounds__(128) macm_observe_kernel(const __grid_constant__ SimConst P)
 {
     constexpr int NC = G * APL;
     constexpr int GPW = 32 / G;
@@ -887,22 +1107,28 @@ __global__ void __launch_bounds__(128) macm_flock_observe_kernel(const __grid_co
     const int slot_in_block = (threadIdx.x >> 5) * GPW + (threadIdx.x & 31) / G;
     const int env = blockIdx.x * (blockDim.x / 32) * GPW + slot_in_block;
     if (env >= P.E) return;
-    EnvS S;
+    EnvS<NC> S;
     S.TC = P.TC;
     S.base = smem_raw + (size_t)slot_in_block * Lay<NC>::bytes(P.TC);
     float ang[APL];
+    uint2 alive = make_uint2(0u, 0u);
 #pragma unroll
     for (int s = 0; s < APL; ++s) {
         const int i = g.gl + s * G;
-        const bool v = i < P.N;
-        const size_t gi = (size_t)env * P.N + (v ? i : 0);
+        const bool ok = i < P.N;
+        const size_t gi = (size_t)env * P.N + (ok ? i : 0);
         const float4 pv = P.posvel[gi];
         ang[s] = P.angsleep[gi].x;
-        S.px<NC>()[i] = v ? pv.x : 3.0e30f;
-        S.py<NC>()[i] = v ? pv.y : 3.0e30f;
+        S.pos()[i] = ok ? make_float2(pv.x, pv.y) : make_float2(3.0e30f, 3.0e30f);
+        S.ang()[i] = ang[s];
+        bool al = ok;
+        if (KIND == MACM_ENV_TDM) al = ok && (__float_as_int(P.tdm[gi].w) & 1);
+        const unsigned bm = g.ballot(al);
+        if (s == 0) alive.x = bm; else alive.y = bm;
     }
     g.sync();
-    flock_observe<G, APL>(g, S, P, env, ang);
+    if (KIND == MACM_ENV_TDM) tdm_observe<G, APL>(g, S, P, env, alive);
+    else flock_observe<G, APL>(g, S, P, env, ang);
 }
 
 // Body creation for every agent (mvmnt.py:61-76): fat AABB = tight +- b2_aabbExtension, awake,
@@ -921,7 +1147,7 @@ __global__ void macm_reset_kernel(const __grid_constant__ SimConst P)
     P.angsleep[gi] = as;
     P.rewards[gi] = 0.0f;
     P.collided[gi] = 0;
-    if (P.kind == MACM_ENV_TDM) P.tdm[gi] = make_float4(P.init_health, __int_as_float(0), __int_as_float(0), 1.0f);
+    if (P.kind == MACM_ENV_TDM) P.tdm[gi] = make_float4(P.init_health, __int_as_float(0), __int_as_float(0), __int_as_float(1));
     if (gi % P.N == 0) {
         const size_t e = gi / P.N;
         P.c_cnt[e] = 0;
@@ -930,24 +1156,24 @@ __global__ void macm_reset_kernel(const __grid_constant__ SimConst P)
     }
 }
 
-template <int G, int APL>
-cudaError_t launch_flock(const SimConst& P, const LaunchCfg& cfg, const void* actions, cudaStream_t s, bool observe_only)
+template <int G, int APL, int KIND>
+cudaError_t launch_one(const SimConst& P, const LaunchCfg& cfg, const void* actions, cudaStream_t s, bool observe_only)
 {
-    if (observe_only) macm_flock_observe_kernel<G, APL><<<cfg.blocks, cfg.threads, cfg.smem_bytes, s>>>(P);
-    else macm_flock_step_kernel<G, APL><<<cfg.blocks, cfg.threads, cfg.smem_bytes, s>>>(P, actions);
+    if (observe_only) macm_observe_kernel<G, APL, KIND><<<cfg.blocks, cfg.threads, cfg.smem_bytes, s>>>(P);
+    else macm_step_kernel<G, APL, KIND><<<cfg.blocks, cfg.threads, cfg.smem_bytes, s>>>(P, actions);
     return cudaGetLastError();
 }
 
-template <int G, int APL>
-cudaError_t prepare_flock(const LaunchCfg& cfg, int* blocks_per_sm)
+template <int G, int APL, int KIND>
+cudaError_t prepare_one(const LaunchCfg& cfg, int* blocks_per_sm)
 {
-    cudaError_t e = cudaFuncSetAttribute(macm_flock_step_kernel<G, APL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(macm_step_kernel<G, APL, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          cfg.smem_bytes);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(macm_flock_observe_kernel<G, APL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(macm_observe_kernel<G, APL, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              cfg.smem_bytes);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, macm_flock_step_kernel<G, APL>, cfg.threads,
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, macm_step_kernel<G, APL, KIND>, cfg.threads,
                                                          cfg.smem_bytes);
 }
 
@@ -982,34 +1208,38 @@ cudaError_t macm_launch_cfg(const SimConst& P, LaunchCfg* cfg)
     return cfg->smem_bytes <= 227 * 1024 ? cudaSuccess : cudaErrorInvalidConfiguration;
 }
 
-#define DISPATCH_SHAPE(CALL)                                   \
-    switch (cfg.G * 8 + cfg.APL) {                             \
-        case 4 * 8 + 1: return CALL(4, 1);                     \
-        case 8 * 8 + 1: return CALL(8, 1);                     \
-        case 16 * 8 + 1: return CALL(16, 1);                   \
-        case 32 * 8 + 1: return CALL(32, 1);                   \
-        case 32 * 8 + 2: return CALL(32, 2);                   \
-        default: return cudaErrorInvalidConfiguration;         \
+#define DISPATCH_SHAPE(CALL)                                                        \
+    switch ((cfg.G * 8 + cfg.APL) * 2 + (P.kind == MACM_ENV_TDM ? 1 : 0)) {         \
+        case (4 * 8 + 1) * 2: return CALL(4, 1, MACM_ENV_FLOCK);                    \
+        case (8 * 8 + 1) * 2: return CALL(8, 1, MACM_ENV_FLOCK);                    \
+        case (16 * 8 + 1) * 2: return CALL(16, 1, MACM_ENV_FLOCK);                  \
+        case (32 * 8 + 1) * 2: return CALL(32, 1, MACM_ENV_FLOCK);                  \
+        case (32 * 8 + 2) * 2: return CALL(32, 2, MACM_ENV_FLOCK);                  \
+        case (4 * 8 + 1) * 2 + 1: return CALL(4, 1, MACM_ENV_TDM);                  \
+        case (8 * 8 + 1) * 2 + 1: return CALL(8, 1, MACM_ENV_TDM);                  \
+        case (16 * 8 + 1) * 2 + 1: return CALL(16, 1, MACM_ENV_TDM);                \
+        case (32 * 8 + 1) * 2 + 1: return CALL(32, 1, MACM_ENV_TDM);                \
+        case (32 * 8 + 2) * 2 + 1: return CALL(32, 2, MACM_ENV_TDM);                \
+        default: return cudaErrorInvalidConfiguration;                              \
     }
 
 cudaError_t macm_prepare_kernels(const SimConst& P, const LaunchCfg& cfg, int* blocks_per_sm)
 {
-    (void)P;
-#define CALL(G_, A_) prepare_flock<G_, A_>(cfg, blocks_per_sm)
+#define CALL(G_, A_, K_) prepare_one<G_, A_, K_>(cfg, blocks_per_sm)
     DISPATCH_SHAPE(CALL)
 #undef CALL
 }
 
 cudaError_t macm_launch_step(const SimConst& P, const LaunchCfg& cfg, const void* actions, cudaStream_t s)
 {
-#define CALL(G_, A_) launch_flock<G_, A_>(P, cfg, actions, s, false)
+#define CALL(G_, A_, K_) launch_one<G_, A_, K_>(P, cfg, actions, s, false)
     DISPATCH_SHAPE(CALL)
 #undef CALL
 }
 
 cudaError_t macm_launch_observe(const SimConst& P, const LaunchCfg& cfg, cudaStream_t s)
 {
-#define CALL(G_, A_) launch_flock<G_, A_>(P, cfg, nullptr, s, true)
+#define CALL(G_, A_, K_) launch_one<G_, A_, K_>(P, cfg, nullptr, s, true)
     DISPATCH_SHAPE(CALL)
 #undef CALL
 }

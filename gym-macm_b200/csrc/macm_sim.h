@@ -38,6 +38,8 @@ struct SimConst {
     double force_pen;   // agent_force * (1 - percent_mov_penalty) (combat.py:46-49)
     double diag;        // 1/np.sqrt(2)                          (mvmnt.py:112)
     double melee_range; // combat.py:22,145
+    double melee_dmg_d; // combat.py:23,153 (health arithmetic is float64 in the reference)
+    const double2* sincos_tab;  // [418] sin,cos(k/128): library-owned, filled at macm_create
     // state
     float4* posvel; float2* angsleep; float4* fat;
     uint32_t* c_ab; float2* c_imp; int* c_cnt; int4* env_state;

@@ -123,7 +123,7 @@ typedef struct macm_buffers {
     int32_t* env_state;       /* [E,4]   step_count, MACM_ENV_* bits, touching contacts of the last step, winner (TDM; -1)  16-byte aligned */
     float* targets;           /* [E,T,2] Flock target positions (mvmnt.py:47-52)  8-byte aligned */
     uint8_t* target_idx;      /* [N]     targets_idx (mvmnt.py:43), shared by all envs */
-    float* tdm_state;         /* [E,N,4] TDM: health, cooldown_atk steps left (int bits), cooldown_mov steps left (int bits), alive (0/1)  16-byte aligned */
+    float* tdm_state;         /* [E,N,4] TDM: health, cooldown_atk steps left (int bits), cooldown_mov steps left (int bits), alive | hits_taken<<8 (int bits)  16-byte aligned */
     uint8_t* team;            /* [N]     TDM: team of agent i, shared by all envs */
     /* ---- outputs (written by macm_step / macm_observe) ---- */
     float* obs;               /* Flock polar [E,N,4] = nn_dist nn_theta tgt_r tgt_theta;
