@@ -261,17 +261,31 @@ def main():
 
     # ---- end to end through the host-buffer entry point (macm_step_host) --------------------
     e2e = None
-    s0 = sims[0]
-    pin = s0.engine.pinned()
-    host_actions = [acts[i].cpu().pin_memory() for i in range(4)]
-    for k in range(3):
-        s0.engine.step_host(host_actions[k % 4], want=("obs", "rewards", "done"))
+    # two batches in ping-pong (the usual double-buffered rollout): while one batch's observations
+    # travel to the host, the other batch steps.  Every step still pays its own H2D of actions and
+    # D2H of obs + rewards + done inside the timed region.
+    pp = sims[:2]
+    want = ("obs", "rewards", "done")
+    pin = pp[0].engine.pinned()
+    host_actions = [acts[i].cpu() for i in range(4)]
+    for s_ in pp:
+        for k in range(3):
+            s_.engine.pinned()["actions"].copy_(host_actions[k % 4])
+            s_.engine.step_host(s_.engine.pinned()["actions"], want=want)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    checksum = 0.0
     te = time.perf_counter()
     for k in range(args.e2e_steps):
-        sims[k % ROT].engine.step_host(host_actions[k % 4], want=("obs", "rewards", "done"))
+        cur = pp[k % 2].engine
+        if k >= 2:
+            cur.host_sync()                                   # results of this batch's previous step
+            checksum += float(cur.pinned()["rewards"][0, 0])  # the host reads them
+        cur.pinned()["actions"].copy_(host_actions[k % 4])    # this step's actions, written by the host
+        cur.step_host(cur.pinned()["actions"], want=want, wait=False)
+    for s_ in pp:
+        s_.engine.host_sync()
     el = time.perf_counter() - te
     if world > 1:
         t = torch.tensor([el], device=dev, dtype=torch.float64)
@@ -281,7 +295,8 @@ def main():
     d2h = int(sum(pin[k].numel() * pin[k].element_size() for k in ("obs", "rewards", "done")))
     e2e = {"value": world * E * N * args.e2e_steps / el, "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
-           "path": "macm_step_host: pinned host actions -> device, step kernel, obs+rewards+done -> pinned host, sync"}
+           "path": "macm_step_host_async/macm_host_sync on two batches in ping-pong: pinned host actions -> device, "
+                   "step kernel, obs+rewards+done -> pinned host"}
 
     if rank == 0:
         cpu = None

@@ -346,8 +346,8 @@ extern "C" int macm_bot_actions(macm_sim* sim, int policy, uint64_t seed, void* 
     return MACM_OK;
 }
 
-extern "C" int macm_step_host(macm_sim* sim, const void* actions, float* obs, float* rewards, int32_t* nn_idx,
-                              uint8_t* collided, uint8_t* done)
+extern "C" int macm_step_host_async(macm_sim* sim, const void* actions, float* obs, float* rewards, int32_t* nn_idx,
+                                    uint8_t* collided, uint8_t* done)
 {
     if (!sim || !actions) return MACM_E_INVALID;
     if (!sim->bound) return MACM_E_UNBOUND;
@@ -358,7 +358,6 @@ extern "C" int macm_step_host(macm_sim* sim, const void* actions, float* obs, fl
     if (!sim->hstream) CU(cudaStreamCreateWithFlags(&sim->hstream, cudaStreamNonBlocking));
     if (sim->d_actions_bytes < abytes) {
         if (sim->d_actions) cudaFree(sim->d_actions);
-    if (sim->d_sincos) cudaFree(sim->d_sincos);
         sim->d_actions = nullptr;
         sim->d_actions_bytes = 0;
         CU(cudaMalloc(&sim->d_actions, abytes));
@@ -373,8 +372,21 @@ extern "C" int macm_step_host(macm_sim* sim, const void* actions, float* obs, fl
     if (nn_idx && sim->K.nn_idx) CU(cudaMemcpyAsync(nn_idx, sim->K.nn_idx, z.nn_idx, cudaMemcpyDeviceToHost, s));
     if (collided) CU(cudaMemcpyAsync(collided, sim->K.collided, z.collided, cudaMemcpyDeviceToHost, s));
     if (done) CU(cudaMemcpyAsync(done, sim->K.done, z.done, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
     return MACM_OK;
+}
+
+extern "C" int macm_host_sync(macm_sim* sim)
+{
+    if (!sim) return MACM_E_INVALID;
+    if (sim->hstream) CU(cudaStreamSynchronize(sim->hstream));
+    return MACM_OK;
+}
+
+extern "C" int macm_step_host(macm_sim* sim, const void* actions, float* obs, float* rewards, int32_t* nn_idx,
+                              uint8_t* collided, uint8_t* done)
+{
+    const int rc = macm_step_host_async(sim, actions, obs, rewards, nn_idx, collided, done);
+    return rc != MACM_OK ? rc : macm_host_sync(sim);
 }
 
 extern "C" int macm_host_alloc(void** out, uint64_t bytes)

@@ -56,7 +56,8 @@ class MacmLaunchInfo(C.Structure):
 
 EXPORTS = ("macm_abi_version", "macm_strerror", "macm_last_cuda_error", "macm_params_default", "macm_create",
            "macm_destroy", "macm_get_buffer_sizes", "macm_get_launch_info", "macm_bind", "macm_reset",
-           "macm_sample_reset", "macm_step", "macm_observe", "macm_bot_actions", "macm_step_host", "macm_host_alloc",
+           "macm_sample_reset", "macm_step", "macm_observe", "macm_bot_actions", "macm_step_host", "macm_step_host_async", "macm_host_sync",
+           "macm_host_alloc",
            "macm_host_free", "macm_launch_count")
 
 
@@ -93,6 +94,8 @@ def lib():
         L.macm_observe.argtypes = [vp, vp]
         L.macm_bot_actions.argtypes = [vp, C.c_int, u64, vp, vp]
         L.macm_step_host.argtypes = [vp] * 7
+        L.macm_step_host_async.argtypes = [vp] * 7
+        L.macm_host_sync.argtypes = [vp]
         L.macm_host_alloc.argtypes = [C.POINTER(vp), u64]
         L.macm_host_free.argtypes = [vp]
         L.macm_launch_count.restype = C.c_int64

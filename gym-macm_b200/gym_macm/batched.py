@@ -52,6 +52,30 @@ def flock_params(settings, n_envs, n_agents, n_targets):
     return p
 
 
+def tdm_params(settings, n_envs, n_agents):
+    """combatSettings (+ combat.Agent constants) -> macm_params."""
+    p = _lib.default_params(_lib.TDM)
+    fx = settings.bodySettings["fixtures"]
+    p.n_envs, p.n_agents, p.n_targets = int(n_envs), int(n_agents), 0
+    p.max_contacts, p.max_touching = int(settings.max_contacts), int(settings.max_touching)
+    p.hz = float(settings.hz)
+    p.velocity_iterations = int(settings.velocityIterations)
+    p.position_iterations = int(settings.positionIterations)
+    p.warm_starting = int(bool(settings.enableWarmStarting))
+    p.damping_model = _lib.DAMPING[str(settings.damping_model)]
+    p.radius, p.density, p.friction = float(fx.radius), float(fx.density), float(fx.friction)
+    p.linear_damping = float(settings.bodySettings["linearDamping"])
+    p.agent_force = float(settings.agent_force)
+    p.agent_rotation_speed = float(settings.agent_rotation_speed)
+    p.time_limit = float(settings.time_limit)
+    p.flags = 1 if settings.repair_mov_cooldown else 0
+    p.cooldown_atk, p.cooldown_mov_penalty = float(settings.cooldown_atk), float(settings.cooldown_mov_penalty)
+    p.melee_range, p.melee_dmg = float(settings.melee_range), float(settings.melee_dmg)
+    p.percent_mov_penalty, p.init_health = float(settings.percent_mov_penalty), float(settings.init_health)
+    p.world_width, p.world_height = float(settings.world_width), float(settings.world_height)
+    return p
+
+
 class Engine(object):
     """A macm_sim handle plus the torch tensors bound to it."""
 
@@ -144,15 +168,21 @@ class Engine(object):
             self._pinned = p
         return self._pinned
 
-    def step_host(self, actions_host, want=("obs", "rewards", "nn_idx", "collided", "done")):
-        """macm_step_host: host actions in, host outputs out; the copies are part of the call."""
+    def step_host(self, actions_host, want=("obs", "rewards", "nn_idx", "collided", "done"), wait=True):
+        """macm_step_host: host actions in, host outputs out; the copies are part of the call.
+        wait=False enqueues on the handle's stream (macm_step_host_async); call host_sync() before
+        reading the returned pinned tensors."""
         p = self.pinned()
         if actions_host.data_ptr() != p["actions"].data_ptr():
             p["actions"].copy_(actions_host)
         ptr = lambda n: C.c_void_p(p[n].data_ptr()) if (n in want and n in p) else None
-        _lib.check(_lib.lib().macm_step_host(self._h, C.c_void_p(p["actions"].data_ptr()), ptr("obs"), ptr("rewards"),
-                                            ptr("nn_idx"), ptr("collided"), ptr("done")), self._h)
+        fn = _lib.lib().macm_step_host if wait else _lib.lib().macm_step_host_async
+        _lib.check(fn(self._h, C.c_void_p(p["actions"].data_ptr()), ptr("obs"), ptr("rewards"),
+                      ptr("nn_idx"), ptr("collided"), ptr("done")), self._h)
         return p
+
+    def host_sync(self):
+        _lib.check(_lib.lib().macm_host_sync(self._h), self._h)
 
     @property
     def launch_count(self):
@@ -305,6 +335,125 @@ class BatchedFlock(object):
         ab = t["contact_ab"][env, :n].cpu().numpy().astype(np.uint32)
         imp = t["contact_imp"][env, :n].cpu().numpy()
         return np.stack([ab & 0xff, (ab >> 8) & 0xff], -1).astype(np.int32), ((ab >> 16) & 1).astype(np.uint8), imp
+
+    def close(self):
+        self.engine.close()
+
+
+class BatchedTDM(object):
+    """E independent team-deathmatch environments (gym_macm/envs/combat.py) on one GPU, with the
+    repaired semantics of SURVEY.md Appendix B (the reference class cannot be constructed as
+    shipped).  `n_agents=[15, 15, 15]` gives three teams; agent index = team-major order, the
+    reference's ids are `str(team) + str(j)` (combat.py:87).
+
+        obs = {"myHealth": float32 [E,N], "myTeam": uint8 [N], "alive": bool [E,N],
+               "agents": {"type": float32 [E,N,N] (1 ally, 0 enemy, -1 no entry),
+                          "position": float32 [E,N,N,3] = r, theta, phi}}       (combat.py:211-226)
+
+    `step(actions)`: uint8 [E,N,4] = a0, a1, a2, attack (or any integer tensor of that shape);
+    returns `(obs, rewards)`; rewards are -1 for an alive agent listed in a contact, else 0 (B12).
+    """
+
+    name = "Team Deathmatch (batched)"
+
+    def __init__(self, n_envs, n_agents=[1, 1], actors=None, colors=None, device=None, seed=0, **kwargs):
+        self.settings = combatSettings(**kwargs)
+        self.n_agents = _as_list(n_agents)
+        self.n_envs = int(n_envs)
+        self.teams = [t for t, n in enumerate(self.n_agents) for _ in range(n)]
+        self.ids = [str(t) + str(j) for t, n in enumerate(self.n_agents) for j in range(n)]
+        N = len(self.teams)
+        if len(self.n_agents) > 8:
+            raise ValueError("at most 8 teams")
+        self.actors, self.colors = actors, colors
+        self.engine = Engine(tdm_params(self.settings, self.n_envs, N), device)
+        torch = _torch()
+        self.engine.t["team"].copy_(torch.tensor(self.teams, dtype=torch.uint8))
+        self.agents = list(range(N))
+        self._act4 = None
+        if seed is not None:
+            self.reset(seed)
+
+    @property
+    def device(self):
+        return self.engine.device
+
+    @property
+    def state(self):
+        return self.engine.t
+
+    @property
+    def done(self):
+        return self.engine.t["done"].bool()
+
+    @property
+    def winner(self):
+        return self.engine.t["env_state"][:, 3]
+
+    @property
+    def step_count(self):
+        return self.engine.t["env_state"][:, 0]
+
+    @property
+    def alive(self):
+        return (self.engine.t["tdm_state"][..., 3].view(_torch().int32) & 1).bool()
+
+    @property
+    def health(self):
+        return self.engine.t["tdm_state"][..., 0]
+
+    @property
+    def cooldowns(self):
+        """(attack, movement-penalty) cool-downs as whole steps left."""
+        ts = self.engine.t["tdm_state"].view(_torch().int32)
+        return ts[..., 1], ts[..., 2]
+
+    def reset(self, seed=0):
+        """Fresh worlds drawn on the device from combat.py:84-86."""
+        self.engine.sample_reset(seed)
+        return self.obs
+
+    def load_state(self, pos, angle, vel=None):
+        torch = _torch()
+        t = self.engine.t
+        E, N = self.engine.E, self.engine.N
+        t["posvel"][..., 0:2] = torch.as_tensor(pos, dtype=torch.float32).reshape(E, N, 2).to(self.device)
+        t["posvel"][..., 2:4] = 0 if vel is None else torch.as_tensor(vel, dtype=torch.float32).reshape(E, N, 2).to(self.device)
+        t["angsleep"][..., 0] = torch.as_tensor(angle, dtype=torch.float32).reshape(E, N).to(self.device)
+        self.engine.reset()
+        return self.obs
+
+    @property
+    def obs(self):
+        o = self.engine.t["obs"].view(self.engine.E, self.engine.N, self.engine.N, 4)
+        return {"myHealth": self.health, "myTeam": self.engine.t["team"], "alive": self.alive,
+                "agents": {"type": o[..., 3], "position": o[..., 0:3]}}
+
+    @property
+    def rewards(self):
+        return self.engine.t["rewards"]
+
+    def step(self, actions):
+        torch = _torch()
+        E, N = self.engine.E, self.engine.N
+        a = actions
+        if not (torch.is_tensor(a) and a.dtype == torch.uint8 and a.is_cuda and tuple(a.shape) == (E, N, 4)
+                and a.is_contiguous()):
+            if self._act4 is None:
+                self._act4 = torch.zeros((E, N, 4), dtype=torch.uint8, device=self.device)
+            self._act4.copy_(torch.as_tensor(actions, device=self.device).reshape(E, N, 4))
+            a = self._act4
+        self.engine.step(a)
+        return self.obs, self.engine.t["rewards"]
+
+    def bot_actions(self, policy="random", seed=0, out=None):
+        torch = _torch()
+        if out is None:
+            out = torch.empty((self.engine.E, self.engine.N, 4), dtype=torch.uint8, device=self.device)
+        self.engine.bot_actions(_lib.BOTS[policy], seed, out)
+        return out
+
+    contacts = BatchedFlock.contacts
 
     def close(self):
         self.engine.close()

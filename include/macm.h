@@ -207,6 +207,13 @@ int macm_bot_actions(macm_sim* sim, int policy, uint64_t seed, void* actions_out
  * waits.  Pinned host memory (macm_host_alloc) makes the copies asynchronous DMA. */
 int macm_step_host(macm_sim* sim, const void* actions, float* obs, float* rewards, int32_t* nn_idx,
                    uint8_t* collided, uint8_t* done);
+/* The same work enqueued on the handle's own stream without waiting: with pinned host buffers the
+ * copies and the kernel of one batch overlap those of another batch (two handles in ping-pong).
+ * The outputs are valid after macm_host_sync(sim).  The host state (bound device buffers) of a
+ * handle must not be touched from other streams between the two calls. */
+int macm_step_host_async(macm_sim* sim, const void* actions, float* obs, float* rewards, int32_t* nn_idx,
+                         uint8_t* collided, uint8_t* done);
+int macm_host_sync(macm_sim* sim);
 int macm_host_alloc(void** out, uint64_t bytes);
 int macm_host_free(void* p);
 
