@@ -111,6 +111,7 @@ static int derive_constants(macm_sim* sim)
     SimConst& K = sim->K;
     memset(&K, 0, sizeof(K));
     K.E = p.n_envs; K.N = p.n_agents; K.T = p.n_targets;
+    K.env_base = p.env_index_base;
     const int pairs = p.n_agents * (p.n_agents - 1) / 2;
     int C = p.max_contacts > 0 ? p.max_contacts : (pairs < 8 * p.n_agents ? pairs : 8 * p.n_agents);
     if (C > pairs) C = pairs;

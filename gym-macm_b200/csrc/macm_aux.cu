@@ -36,8 +36,9 @@ __global__ void macm_sample_kernel(const __grid_constant__ SimConst P, uint64_t 
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t EN = (uint64_t)P.E * P.N, ET = (uint64_t)P.E * P.T;
     if (idx < EN) {
-        const Philox r(seed, idx, 0u, 0u);
-        const Philox r2(seed, idx, 0u, 1u);
+        const uint64_t gidx = idx + (uint64_t)P.env_base * P.N;   // global agent index
+        const Philox r(seed, gidx, 0u, 0u);
+        const Philox r2(seed, gidx, 0u, 1u);
         const int i = (int)(idx % P.N);
         double x, y;
         if (P.kind == MACM_ENV_FLOCK) {
@@ -52,7 +53,7 @@ __global__ void macm_sample_kernel(const __grid_constant__ SimConst P, uint64_t 
         P.angsleep[idx] = make_float2((float)a, 0.0f);
     } else if (idx < EN + ET) {
         const uint64_t t = idx - EN;
-        const Philox r(seed, t, 1u, 0u);
+        const Philox r(seed, t + (uint64_t)P.env_base * P.T, 1u, 0u);
         const double ang = 2 * NP_PI * r.u53(0);              // mvmnt.py:50-52
         const double dist = tmin + r.u53(1) * (tmax - tmin);
         reinterpret_cast<float2*>(const_cast<float2*>(P.targets))[t] =
@@ -72,7 +73,7 @@ __global__ void macm_bot_kernel(const __grid_constant__ SimConst P, int policy, 
         case MACM_BOT_DIAG: a0 = 2; a1 = 2; break;
         case MACM_BOT_RANDOM: {
             const int step = P.env_state[gi / P.N].x;
-            const Philox r(seed, gi, 2u, (uint32_t)step);
+            const Philox r(seed, gi + (uint64_t)P.env_base * P.N, 2u, (uint32_t)step);
             a0 = (uint32_t)(((uint64_t)r.c[0] * 3u) >> 32);
             a1 = (uint32_t)(((uint64_t)r.c[1] * 3u) >> 32);
             a2 = (uint32_t)(((uint64_t)r.c[2] * 3u) >> 32);

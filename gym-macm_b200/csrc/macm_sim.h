@@ -24,6 +24,7 @@ struct SimConst {
     int E, N, T, C, TC;
     int kind, reward_mode, action_mode, coord, vel_iters, pos_iters, warm_starting, flags;
     int done_step, cd_atk_steps, cd_mov_steps, obs_dim;
+    int env_base;       // global index of this handle's env 0 (keys the counter-based samplers)
     float h;            // (float)(1/hz): timeStep at the SWIG boundary (cm_framework.py:182,222)
     float dt_ratio;     // fl(fl(1/h) * h): b2TimeStep::dtRatio once inv_dt0 != 0
     float inv_mass;     // 1 / (density * b2_pi * r * r)

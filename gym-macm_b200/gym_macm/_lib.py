@@ -32,6 +32,7 @@ class MacmParams(C.Structure):
         ("percent_mov_penalty", f64), ("init_health", f64),
         ("start_spread", f64), ("start_x", f64), ("start_y", f64), ("target_mindist", f64), ("target_maxdist", f64),
         ("world_width", f64), ("world_height", f64),
+        ("env_index_base", i32), ("reserved0", i32),
     ]
 
 

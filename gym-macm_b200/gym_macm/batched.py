@@ -49,6 +49,7 @@ def flock_params(settings, n_envs, n_agents, n_targets):
     p.start_spread = float(settings.start_spread)
     p.start_x, p.start_y = float(settings.start_point[0]), float(settings.start_point[1])
     p.target_mindist, p.target_maxdist = float(settings.target_mindist), float(settings.target_maxdist)
+    p.env_index_base = int(settings.env_index_base)
     return p
 
 
@@ -73,6 +74,7 @@ def tdm_params(settings, n_envs, n_agents):
     p.melee_range, p.melee_dmg = float(settings.melee_range), float(settings.melee_dmg)
     p.percent_mov_penalty, p.init_health = float(settings.percent_mov_penalty), float(settings.init_health)
     p.world_width, p.world_height = float(settings.world_width), float(settings.world_height)
+    p.env_index_base = int(settings.env_index_base)
     return p
 
 

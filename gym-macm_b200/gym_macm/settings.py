@@ -63,6 +63,7 @@ class _EnvSettings(fwSettings):
         self.damping_model = "taylor"      # "taylor": Box2D <= 2.3.0, "pade": >= 2.3.1
         self.max_contacts = 0              # 0 = library default
         self.max_touching = 0
+        self.env_index_base = 0            # global index of this batch's env 0 (gym_macm.dist shards)
 
 
 class flockSettings(_EnvSettings):

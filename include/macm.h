@@ -109,6 +109,8 @@ typedef struct macm_params {
     double target_maxdist;        /* settings.py:140  60 */
     double world_width;           /* combat.py:76     30   TDM: x = U * (team + width/2), y = U * height */
     double world_height;          /* combat.py:77     30 */
+    int32_t env_index_base;       /* global index of env 0 of this handle (shards of one batch); keys the samplers */
+    int32_t reserved0;
 } macm_params;
 
 /* Caller-owned device buffers.  E = n_envs, N = n_agents, T = n_targets, C = max_contacts. */
