@@ -149,13 +149,38 @@ __device__ __forceinline__ float wrap_pi_f(float t)
     return t;
 }
 
+// atan2 for the observation outputs (fp32, reference: float64 np.arctan2): octant reduction +
+// degree-15 odd minimax polynomial, max error 1.3e-7 rad over the reduced range (measured against
+// float64 atan with the float32 evaluation order below); tests allow 3e-6.
+__device__ __forceinline__ float fast_atan2f(float y, float x)
+{
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float a = mx > 0.0f ? __fdividef(mn, mx) : 0.0f;
+    const float q = a * a;
+    float r = -0.0040545230731368065f;
+    r = fmaf(r, q, 0.02186279185116291f);
+    r = fmaf(r, q, -0.0559120774269104f);
+    r = fmaf(r, q, 0.09642177820205688f);
+    r = fmaf(r, q, -0.13908621668815613f);
+    r = fmaf(r, q, 0.19946564733982086f);
+    r = fmaf(r, q, -0.33329859375953674f);
+    r = fmaf(r, q, 0.9999993443489075f);
+    r = r * a;
+    if (ay > ax) r = 1.5707963267948966f - r;
+    if (x < 0.0f) r = 3.14159265358979f - r;
+    return copysignf(r, y);
+}
+
+__device__ __noinline__ void sincos_slow(float Af, double* s, double* c) { sincos((double)Af, s, c); }
+
 // sin and cos of a float32 angle to ~1 ulp of float64.  A = k/128 + x with |x| <= 2^-8 (exact
 // split, A is a float): table of sin/cos(k/128) (host-computed doubles) + degree-7/8 Taylor.
 // Outside the table (|A| > 3.25, only reachable through load_state) falls back to sincos().
 __device__ __forceinline__ void sincos_f32arg(const double2* __restrict__ tab, float Af, double& s, double& c)
 {
     const float fk = rintf(fabsf(Af) * 128.0f);
-    if (!(fk <= 416.0f)) { sincos((double)Af, &s, &c); return; }
+    if (!(fk <= 416.0f)) { sincos_slow(Af, &s, &c); return; }
     const double2 sc = __ldg(&tab[(int)fk]);
     const double x = fabs((double)Af) - (double)fk * 0.0078125;
     const double x2 = x * x;
@@ -324,26 +349,41 @@ __device__ int find_new_contacts(const Grp<G>& g, const EnvS<G * APL>& S, const 
 // ------------------------------------------------------------------------------------------
 // observation pass for the agents a lane owns (Flock.get_obs, mvmnt.py:181-222)
 // ------------------------------------------------------------------------------------------
+// cartesian variant of the observation record (coord == "cartesian", mvmnt.py:202-203,215-216); cold
+__device__ __noinline__ void store_cartesian(float* obs, size_t gi, float nn_d, float nn_t, float tg_r, float tg_t)
+{
+    float sn, cn, st, ct;
+    sincosf(nn_t, &sn, &cn);
+    sincosf(tg_t, &st, &ct);
+    float2* ob = reinterpret_cast<float2*>(obs) + gi * 3;
+    ob[0] = make_float2(nn_d, cn);
+    ob[1] = make_float2(sn, tg_r);
+    ob[2] = make_float2(ct, st);
+}
+
 template <int G, int APL>
 __device__ void flock_observe(const Grp<G>& g, const EnvS<G * APL>& S, const SimConst& P, int env, const float* ang)
 {
     const float2* pos = S.pos();
     const int N = P.N;
-    float2 o[APL];
+    float2 o[APL], tg[APL];
     float best[APL];
     int bi[APL];
 #pragma unroll
     for (int s = 0; s < APL; ++s) {
-        o[s] = pos[g.gl + s * G];
+        const int i = g.gl + s * G;
+        o[s] = pos[i];
         best[s] = __int_as_float(0x7f800000);
         bi[s] = -1;
+        // issued before the search so that the latency hides behind it
+        tg[s] = P.targets[(size_t)env * P.T + P.target_idx[i < N ? i : 0]];
     }
     // nearest other agent: strict '<' over ascending j keeps the lowest index on ties (mvmnt.py:194).
     // Slot s only has to skip itself while j runs through its own 32-block.
 #pragma unroll
     for (int jb = 0; jb < G * APL; jb += G) {
         const int jend = (N - jb) < G ? (N - jb) : G;
-#pragma unroll 8
+#pragma unroll 4
         for (int jj = 0; jj < jend; ++jj) {
             const float2 q = pos[jb + jj];
             const bool notme = jj != g.gl;
@@ -366,24 +406,14 @@ __device__ void flock_observe(const Grp<G>& g, const EnvS<G * APL>& S, const Sim
         if (bi[s] >= 0) {
             const float2 q = pos[bi[s]];
             nn_d = sqrtf(best[s]);
-            nn_t = wrap_pi_f(atan2f(q.y - o[s].y, q.x - o[s].x) - ang[s]);
+            nn_t = wrap_pi_f(fast_atan2f(q.y - o[s].y, q.x - o[s].x) - ang[s]);
         }
-        const float2 tg = P.targets[(size_t)env * P.T + P.target_idx[i]];
-        const float tdx = tg.x - o[s].x, tdy = tg.y - o[s].y;
+        const float tdx = tg[s].x - o[s].x, tdy = tg[s].y - o[s].y;
         const float tg_r = sqrtf(tdx * tdx + tdy * tdy);
-        const float tg_t = wrap_pi_f(atan2f(tdy, tdx) - ang[s]);
+        const float tg_t = wrap_pi_f(fast_atan2f(tdy, tdx) - ang[s]);
         P.nn_idx[gi] = bi[s];
-        if (P.coord == MACM_COORD_POLAR) {
-            reinterpret_cast<float4*>(P.obs)[gi] = make_float4(nn_d, nn_t, tg_r, tg_t);
-        } else {
-            float sn, cn, st, ct;
-            sincosf(nn_t, &sn, &cn);
-            sincosf(tg_t, &st, &ct);
-            float2* ob = reinterpret_cast<float2*>(P.obs) + gi * 3;
-            ob[0] = make_float2(nn_d, cn);
-            ob[1] = make_float2(sn, tg_r);
-            ob[2] = make_float2(ct, st);
-        }
+        if (P.coord == MACM_COORD_POLAR) reinterpret_cast<float4*>(P.obs)[gi] = make_float4(nn_d, nn_t, tg_r, tg_t);
+        else store_cartesian(P.obs, gi, nn_d, nn_t, tg_r, tg_t);
     }
 }
 
@@ -420,13 +450,124 @@ __device__ void tdm_observe(const Grp<G>& g, const EnvS<G * APL>& S, const SimCo
             if (ai && j != i && bit_of(alive, j)) {
                 const float dx = o[s].x - p.x, dy = o[s].y - p.y;
                 v.x = sqrtf(dx * dx + dy * dy);
-                v.y = wrap_pi_f(atan2f(dy, dx) - a);
+                v.y = wrap_pi_f(fast_atan2f(dy, dx) - a);
                 v.z = wrap_pi_f(oa[s] - a);
                 v.w = (team[s] == ti) ? 1.0f : 0.0f;
             }
             out[(size_t)i * N + j] = v;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// Generic contact solver for environments with more touching contacts than lanes (tc > G):
+// every ordered contact goes through shared memory, level by level.  Rare (dense piles) and kept
+// out of line so that the common path stays small in the instruction cache.
+// ------------------------------------------------------------------------------------------
+template <int G, int APL>
+__device__ __noinline__ void solve_velocity_big(const Grp<G>& g, const EnvS<G * APL>& S, const SimConst& P, int tc,
+                                                int nlev, float ratio, float2* c_imp)
+{
+    const float2* pos = S.pos(); float2* vel = S.vel();
+    float2* t_n = S.t_n(); float2* t_imp = S.t_imp();
+    const uint32_t* t_ew = S.t_ew();
+    const uint16_t* ordlvl = S.ordlvl();
+    const float mass_n = P.normal_mass, mass_t = P.normal_mass;
+    for (int t = g.gl; t < tc; t += G) {
+        const uint32_t ew = t_ew[t];
+        const float2 pa = pos[EW_A(ew)], pb = pos[EW_B(ew)];
+        float nx = 1.0f, ny = 0.0f;
+        const float dx = pb.x - pa.x, dy = pb.y - pa.y;
+        if ((dx * dx + dy * dy) > B2_EPSILON * B2_EPSILON) { nx = dx; ny = dy; b2normalize(nx, ny); }
+        float2 im = make_float2(0.0f, 0.0f);
+        if (P.warm_starting) { im = t_imp[t]; im.x = ratio * im.x; im.y = ratio * im.y; }
+        t_n[t] = make_float2(nx, ny);
+        t_imp[t] = im;
+    }
+    g.sync();
+    for (int it = -1; it < P.vel_iters; ++it) {   // it == -1: WarmStart
+        for (int lev = 1; lev <= nlev; ++lev) {
+            for (int k = g.gl; k < tc; k += G) {
+                const int ol = ordlvl[k];
+                if ((ol >> 8) != lev) continue;
+                const int t = ol & 0xff;
+                const uint32_t ew = t_ew[t];
+                const int a = EW_A(ew), b = EW_B(ew);
+                const float2 n = t_n[t];
+                float2 im = t_imp[t];
+                float2 va = vel[a], vb = vel[b];
+                if (it < 0) warm_start(n.x, n.y, im.x, im.y, P.inv_mass, va, vb);
+                else solve_velocity(n.x, n.y, P.friction, mass_n, mass_t, P.inv_mass, im.x, im.y, va, vb);
+                vel[a] = va; vel[b] = vb;
+                t_imp[t] = im;
+            }
+            g.sync();
+        }
+    }
+    const uint16_t* t_slot = S.t_slot();
+    for (int t = g.gl; t < tc; t += G) c_imp[t_slot[t]] = t_imp[t];
+}
+
+template <int G, int APL>
+__device__ __noinline__ void solve_position_big(const Grp<G>& g, const EnvS<G * APL>& S, const SimConst& P, int tc,
+                                                int nlev)
+{
+    float2* pos = S.pos();
+    const uint8_t* label = S.label();
+    uint8_t* isl_act = S.isl_act(); uint8_t* isl_bad = S.isl_bad();
+    const uint32_t* t_ew = S.t_ew();
+    const uint16_t* ordlvl = S.ordlvl();
+    for (int it = 0; it < P.pos_iters; ++it) {
+        for (int lev = 1; lev <= nlev; ++lev) {
+            for (int k = g.gl; k < tc; k += G) {
+                const int ol = ordlvl[k];
+                if ((ol >> 8) != lev) continue;
+                const uint32_t ew = t_ew[ol & 0xff];
+                const int a = EW_A(ew), b = EW_B(ew);
+                const int isl = label[a];
+                if (!isl_act[isl]) continue;
+                float2 ca = pos[a], cb = pos[b];
+                const float sep = solve_position(P.radius, P.k_sum, P.inv_mass, ca, cb);
+                pos[a] = ca; pos[b] = cb;
+                if (!(b2min(0.0f, sep) >= -3.0f * B2_LINEAR_SLOP)) isl_bad[isl] = 1;
+            }
+            g.sync();
+        }
+        bool any_bad = false;
+#pragma unroll
+        for (int s = 0; s < APL; ++s) {
+            const int i = g.gl + s * G;
+            const uint8_t bad = isl_bad[i];
+            isl_act[i] = bad;
+            isl_bad[i] = 0;
+            any_bad |= bad != 0;
+        }
+        g.sync();
+        if (!g.ballot(any_bad)) break;
+    }
+}
+
+// b2World::Step prologue of a world with new fixtures: FindNewContacts before Collide.  Runs on
+// the first step after a reset only; out of line.
+template <int G, int APL>
+__device__ __noinline__ int fresh_world_contacts(const Grp<G>& g, const EnvS<G * APL>& S, const SimConst& P, uint2 alive,
+                                                 int cnt, uint32_t* c_ab, float2* c_imp, bool& overflow)
+{
+    uint2* adj = S.adj();
+    for (int base = 0; base < cnt; base += G) {
+        const int k = base + g.gl;
+        if (k < cnt) {
+            const uint32_t ab = c_ab[k];
+            or_bit(adj, ab & 0xff, (ab >> 8) & 0xff);
+            or_bit(adj, (ab >> 8) & 0xff, ab & 0xff);
+        }
+    }
+    g.sync();
+    cnt = find_new_contacts<G, APL>(g, S, P, alive, alive, cnt, c_ab, c_imp, overflow);
+#pragma unroll
+    for (int s = 0; s < APL; ++s) adj[g.gl + s * G] = make_uint2(0u, 0u);
+    g.sync();
+    return cnt;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -635,21 +776,7 @@ __global__ void __launch_bounds__(128) macm_step_kernel(const __grid_constant__ 
     bool overflow_c = false, overflow_t = false;
 
     // ---- phase 2a: new fixtures -> FindNewContacts before Collide (b2World::Step prologue) ----
-    if (es.y & MACM_ENV_FRESH) {
-        for (int base = 0; base < cnt; base += G) {
-            const int k = base + g.gl;
-            if (k < cnt) {
-                const uint32_t ab = c_ab[k];
-                or_bit(adj, ab & 0xff, (ab >> 8) & 0xff);
-                or_bit(adj, (ab >> 8) & 0xff, ab & 0xff);
-            }
-        }
-        g.sync();
-        cnt = find_new_contacts<G, APL>(g, S, P, alive, alive, cnt, c_ab, c_imp, overflow_c);
-#pragma unroll
-        for (int s = 0; s < APL; ++s) adj[g.gl + s * G] = make_uint2(0u, 0u);
-        g.sync();
-    }
+    if (es.y & MACM_ENV_FRESH) cnt = fresh_world_contacts<G, APL>(g, S, P, alive, cnt, c_ab, c_imp, overflow_c);
 
     // ---- phase 2: b2ContactManager::Collide --------------------------------------------------
     // destroy contacts whose fat AABBs stopped overlapping (or whose body was deactivated),
@@ -794,37 +921,30 @@ __global__ void __launch_bounds__(128) macm_step_kernel(const __grid_constant__ 
     }
 
     // ---- phase 5: contact solver, velocity part -------------------------------------------------
-    // Order position k is owned by lane k % G.  The first G positions (all of them, normally)
-    // live in that lane's registers for the whole solve; later ones go through shared memory.
-    const bool has = g.gl < tc;
+    // Order position k is owned by lane k.  With tc <= G (all but dense piles) a lane keeps its
+    // contact in registers for the whole solve; otherwise the generic out-of-line solver runs.
+    const bool big = tc > G;
+    const bool has = !big && g.gl < tc;
     int ka = 0, kb = 0, klv = 0, kt = 0, kisl = 0;
     float knx = 1.0f, kny = 0.0f, knI = 0.0f, ktI = 0.0f;
-    if (tc > 0) {
-        float2* t_n = S.t_n(); float2* t_imp = S.t_imp();
-        const uint32_t* t_ew = S.t_ew();
-        const uint16_t* ordlvl = S.ordlvl();
+    // inv_dt0 == 0 on a world's first step -> dtRatio 0
+    const float ratio = (es.x == 0) ? 0.0f : P.dt_ratio;
+    if (big) {
+        solve_velocity_big<G, APL>(g, S, P, tc, nlev, ratio, c_imp);
+    } else if (tc > 0) {
         const float mass_n = P.normal_mass, mass_t = P.normal_mass;
         // b2ContactSolver ctor + InitializeVelocityConstraints: world manifold at the
         // pre-integration positions, impulses scaled by dtRatio
-        const float ratio = (es.x == 0) ? 0.0f : P.dt_ratio;  // inv_dt0 == 0 on a world's first step
-        for (int k = g.gl; k < tc; k += G) {
-            const int ol = ordlvl[k];
-            const int t = ol & 0xff;
-            const uint32_t ew = t_ew[t];
-            const int a = EW_A(ew), b = EW_B(ew);
-            const float2 pa = pos[a], pb = pos[b];
-            float nx = 1.0f, ny = 0.0f;
+        if (has) {
+            const int ol = S.ordlvl()[g.gl];
+            kt = ol & 0xff; klv = ol >> 8;
+            const uint32_t ew = S.t_ew()[kt];
+            ka = EW_A(ew); kb = EW_B(ew); kisl = label[ka];
+            const float2 pa = pos[ka], pb = pos[kb];
             const float dx = pb.x - pa.x, dy = pb.y - pa.y;
             // b2DistanceSquared(pointA, pointB) is (A - B).(A - B); squares are sign-blind
-            if ((dx * dx + dy * dy) > B2_EPSILON * B2_EPSILON) { nx = dx; ny = dy; b2normalize(nx, ny); }
-            float2 im = make_float2(0.0f, 0.0f);
-            if (P.warm_starting) { im = t_imp[t]; im.x = ratio * im.x; im.y = ratio * im.y; }
-            if (k < G) {
-                kt = t; ka = a; kb = b; klv = ol >> 8; kisl = label[a];
-                knx = nx; kny = ny; knI = im.x; ktI = im.y;
-            } else {
-                t_n[t] = make_float2(nx, ny); t_imp[t] = im;
-            }
+            if ((dx * dx + dy * dy) > B2_EPSILON * B2_EPSILON) { knx = dx; kny = dy; b2normalize(knx, kny); }
+            if (P.warm_starting) { const float2 im = S.t_imp()[kt]; knI = ratio * im.x; ktI = ratio * im.y; }
         }
         if (nlev == 1) {
             // independent contacts: warm start + all iterations without leaving registers
@@ -835,69 +955,22 @@ __global__ void __launch_bounds__(128) macm_step_kernel(const __grid_constant__ 
                     solve_velocity(knx, kny, P.friction, mass_n, mass_t, P.inv_mass, knI, ktI, va, vb);
                 vel[ka] = va; vel[kb] = vb;
             }
-            for (int k = g.gl + G; k < tc; k += G) {
-                const int t = ordlvl[k] & 0xff;
-                const uint32_t ew = t_ew[t];
-                const int a = EW_A(ew), b = EW_B(ew);
-                const float2 n = t_n[t];
-                float2 im = t_imp[t];
-                float2 va = vel[a], vb = vel[b];
-                warm_start(n.x, n.y, im.x, im.y, P.inv_mass, va, vb);
-                for (int it = 0; it < P.vel_iters; ++it)
-                    solve_velocity(n.x, n.y, P.friction, mass_n, mass_t, P.inv_mass, im.x, im.y, va, vb);
-                vel[a] = va; vel[b] = vb;
-                t_imp[t] = im;
-            }
             g.sync();
         } else {
-            // WarmStart, in order
-            for (int lev = 1; lev <= nlev; ++lev) {
-                if (has && klv == lev) {
-                    float2 va = vel[ka], vb = vel[kb];
-                    warm_start(knx, kny, knI, ktI, P.inv_mass, va, vb);
-                    vel[ka] = va; vel[kb] = vb;
-                }
-                for (int k = g.gl + G; k < tc; k += G) {
-                    const int ol = ordlvl[k];
-                    if ((ol >> 8) != lev) continue;
-                    const int t = ol & 0xff;
-                    const uint32_t ew = t_ew[t];
-                    const int a = EW_A(ew), b = EW_B(ew);
-                    const float2 n = t_n[t], im = t_imp[t];
-                    float2 va = vel[a], vb = vel[b];
-                    warm_start(n.x, n.y, im.x, im.y, P.inv_mass, va, vb);
-                    vel[a] = va; vel[b] = vb;
-                }
-                g.sync();
-            }
-            for (int it = 0; it < P.vel_iters; ++it) {
+            for (int it = -1; it < P.vel_iters; ++it) {   // it == -1: WarmStart, in order
                 for (int lev = 1; lev <= nlev; ++lev) {
                     if (has && klv == lev) {
                         float2 va = vel[ka], vb = vel[kb];
-                        solve_velocity(knx, kny, P.friction, mass_n, mass_t, P.inv_mass, knI, ktI, va, vb);
+                        if (it < 0) warm_start(knx, kny, knI, ktI, P.inv_mass, va, vb);
+                        else solve_velocity(knx, kny, P.friction, mass_n, mass_t, P.inv_mass, knI, ktI, va, vb);
                         vel[ka] = va; vel[kb] = vb;
-                    }
-                    for (int k = g.gl + G; k < tc; k += G) {
-                        const int ol = ordlvl[k];
-                        if ((ol >> 8) != lev) continue;
-                        const int t = ol & 0xff;
-                        const uint32_t ew = t_ew[t];
-                        const int a = EW_A(ew), b = EW_B(ew);
-                        const float2 n = t_n[t];
-                        float2 im = t_imp[t];
-                        float2 va = vel[a], vb = vel[b];
-                        solve_velocity(n.x, n.y, P.friction, mass_n, mass_t, P.inv_mass, im.x, im.y, va, vb);
-                        vel[a] = va; vel[b] = vb;
-                        t_imp[t] = im;
                     }
                     g.sync();
                 }
             }
         }
         // StoreImpulses -> manifold (next step's warm start)
-        const uint16_t* t_slot = S.t_slot();
-        if (has) c_imp[t_slot[kt]] = make_float2(knI, ktI);
-        for (int k = g.gl + G; k < tc; k += G) { const int t = ordlvl[k] & 0xff; c_imp[t_slot[t]] = t_imp[t]; }
+        if (has) c_imp[S.t_slot()[kt]] = make_float2(knI, ktI);
     }
 
     // ---- phase 6: integrate positions ------------------------------------------------------------
@@ -925,9 +998,11 @@ __global__ void __launch_bounds__(128) macm_step_kernel(const __grid_constant__ 
     // ---- phase 7: contact solver, position part (per-island early exit) ---------------------------
     {
         uint8_t* isl_act = S.isl_act(); uint8_t* isl_bad = S.isl_bad();
-        if (tc > 0) {
-            const uint32_t* t_ew = S.t_ew();
-            const uint16_t* ordlvl = S.ordlvl();
+        if (big) {
+            solve_position_big<G, APL>(g, S, P, tc, nlev);
+#pragma unroll
+            for (int s = 0; s < APL; ++s) c[s] = pos[g.gl + s * G];
+        } else if (tc > 0) {
             for (int it = 0; it < P.pos_iters; ++it) {
                 for (int lev = 1; lev <= nlev; ++lev) {
                     if (has && klv == lev && isl_act[kisl]) {
@@ -936,18 +1011,6 @@ __global__ void __launch_bounds__(128) macm_step_kernel(const __grid_constant__ 
                         pos[ka] = ca; pos[kb] = cb;
                         // island not solved while min(0, separations) < -3 * linearSlop
                         if (!(b2min(0.0f, sep) >= -3.0f * B2_LINEAR_SLOP)) isl_bad[kisl] = 1;
-                    }
-                    for (int k = g.gl + G; k < tc; k += G) {
-                        const int ol = ordlvl[k];
-                        if ((ol >> 8) != lev) continue;
-                        const uint32_t ew = t_ew[ol & 0xff];
-                        const int a = EW_A(ew), b = EW_B(ew);
-                        const int isl = label[a];
-                        if (!isl_act[isl]) continue;
-                        float2 ca = pos[a], cb = pos[b];
-                        const float sep = solve_position(P.radius, P.k_sum, P.inv_mass, ca, cb);
-                        pos[a] = ca; pos[b] = cb;
-                        if (!(b2min(0.0f, sep) >= -3.0f * B2_LINEAR_SLOP)) isl_bad[isl] = 1;
                     }
                     g.sync();
                 }
