@@ -25,6 +25,10 @@
 
 #include "macm_sim.h"
 
+#ifndef MACM_MIN_BLOCKS
+#define MACM_MIN_BLOCKS 7
+#endif
+
 namespace {
 
 // ------------------------------------------------------------------------------------------
@@ -36,10 +40,15 @@ struct Lay {
     static constexpr int VEL = POS + 8 * NC;      // float2 [NC]  linear velocity
     static constexpr int FAT = VEL + 8 * NC;      // float4 [NC]  fat AABB lo.xy hi.xy
     static constexpr int ADJ = FAT + 16 * NC;     // uint2  [NC]  contact adjacency row (agents 0-31, 32-63)
-    static constexpr int NEW = ADJ + 8 * NC;      // uint2  [NC]  new-pair row being assembled / float4 ray (TDM)
-    static constexpr int ISLMIN = NEW + 8 * NC;   // u32    [NC]  min sleep time of the island seeded here
-    static constexpr int ANG = ISLMIN + 4 * NC;   // float  [NC]  body angle (TDM observation pass)
-    static constexpr int LABEL = ANG + 4 * NC;    // u8     [NC]  island seed of a body
+    // One 8-byte-per-agent scratch region, used by phases that never overlap in time:
+    //   phase 1b  float2 [NC]  far end of an attacker's ray (TDM)
+    //   phase 8   u32    [NC]  min sleep time of the island seeded here            (first half)
+    //   phase 2a/10  uint2 [NC]  new-pair row being assembled (re-zeroed on entry)
+    //   phase 12-13  float [NC]  body angle for the TDM observation pass           (second half)
+    static constexpr int NEW = ADJ + 8 * NC;
+    static constexpr int ISLMIN = NEW;
+    static constexpr int ANG = NEW + 4 * NC;
+    static constexpr int LABEL = NEW + 8 * NC;    // u8     [NC]  island seed of a body
     static constexpr int STACK = LABEL + NC, LASTLVL = STACK + NC, ISLACT = LASTLVL + NC, ISLBAD = ISLACT + NC;
     static constexpr int HEAD = ISLBAD + NC;      // u8     [NC]  newest touching contact of a body
     static constexpr int MISC = (HEAD + NC + 15) / 16 * 16;  // 4 x u32
@@ -574,7 +583,7 @@ __device__ __noinline__ int fresh_world_contacts(const Grp<G>& g, const EnvS<G *
 // the step kernel
 // ------------------------------------------------------------------------------------------
 template <int G, int APL, int KIND>
-__global__ void __launch_bounds__(128) macm_step_kernel(const __grid_constant__ SimConst P,
+__global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const __grid_constant__ SimConst P,
                                                         const void* __restrict__ actions)
 {
     constexpr int NC = G * APL;
@@ -684,7 +693,7 @@ __global__ void __launch_bounds__(128) macm_step_kernel(const __grid_constant__ 
                         cd_atk[s] = P.cd_atk_steps;
                         cd_mov[s] = P.cd_mov_steps;
                         const float dx = (float)(P.melee_range * c1), dy = (float)(P.melee_range * s1);
-                        reinterpret_cast<float4*>(S.nw())[i] = make_float4(c[s].x, c[s].y, c[s].x + dx, c[s].y + dy);
+                        reinterpret_cast<float2*>(S.nw())[i] = make_float2(c[s].x + dx, c[s].y + dy);
                     }
                 } else {
                     cd_atk[s] -= 1;
@@ -714,12 +723,13 @@ __global__ void __launch_bounds__(128) macm_step_kernel(const __grid_constant__ 
 #pragma unroll
         for (int s = 0; s < APL; ++s) { am[s] = g.ballot(attack[s]); any_attack |= am[s] != 0u; }
         if (any_attack) {
-            const float4* ray = reinterpret_cast<const float4*>(S.nw());
+            const float2* ray = reinterpret_cast<const float2*>(S.nw());
 #pragma unroll
             for (int w = 0; w < APL; ++w) {
                 for (unsigned mm = am[w]; mm; mm &= mm - 1) {
                     const int m = w * G + __ffs((int)mm) - 1;
-                    const float4 r4 = ray[m];
+                    const float2 p1 = pos[m], p2 = ray[m];
+                    const float4 r4 = make_float4(p1.x, p1.y, p2.x, p2.y);
                     // b2CircleShape::RayCast against every proxy; keep the smallest fraction,
                     // lowest index among equal fractions
                     unsigned fk[APL];
