@@ -129,6 +129,15 @@ __device__ __forceinline__ void or_bit(uint2* row, int r, int bit)
     atomicOr(bit < 32 ? &row[r].x : &row[r].y, 1u << (bit & 31));
 }
 
+// Packed fp32x2 arithmetic of sm_100 (FADD2 / FMUL2): two IEEE round-to-nearest operations per
+// instruction, bit-identical to the scalar ones.  (A packed multiply feeding a packed add would be
+// contracted into FFMA2 by ptxas even with .rn, so sums of products are finished with scalar adds.)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
 // b2TestOverlap(b2AABB, b2AABB): d1 = b.lo - a.hi, d2 = a.lo - b.hi; overlap iff no component > 0.
 // With IEEE gradual underflow (no -ftz) x - y > 0 <=> x > y, so the subtractions are not needed.
 __device__ __forceinline__ bool aabb_overlap(const float4 a, const float4 b)
@@ -389,20 +398,51 @@ __device__ void flock_observe(const Grp<G>& g, const EnvS<G * APL>& S, const Sim
     }
     // nearest other agent: strict '<' over ascending j keeps the lowest index on ties (mvmnt.py:194).
     // Slot s only has to skip itself while j runs through its own 32-block.
+    if (APL == 2) {
+        // both agents of a lane against candidate j in packed fp32x2: positions are re-staged as
+        // (x, x, y, y) over the fat-AABB region, which is dead by now
+        float4* pos4 = reinterpret_cast<float4*>(S.fat());
+        g.sync();
 #pragma unroll
-    for (int jb = 0; jb < G * APL; jb += G) {
-        const int jend = (N - jb) < G ? (N - jb) : G;
+        for (int s = 0; s < APL; ++s) pos4[g.gl + s * G] = make_float4(o[s].x, o[s].x, o[s].y, o[s].y);
+        g.sync();
+        const f32x2 ox = pack2(o[0].x, o[APL - 1].x), oy = pack2(o[0].y, o[APL - 1].y);
+#pragma unroll
+        for (int jb = 0; jb < G * APL; jb += G) {
+            const int jend = (N - jb) < G ? (N - jb) : G;
 #pragma unroll 4
-        for (int jj = 0; jj < jend; ++jj) {
-            const float2 q = pos[jb + jj];
-            const bool notme = jj != g.gl;
+            for (int jj = 0; jj < jend; ++jj) {
+                const float4 q = pos4[jb + jj];
+                const bool notme = jj != g.gl;
+                const f32x2 dx = sub2(pack2(q.x, q.y), ox), dy = sub2(pack2(q.z, q.w), oy);
+                float xl, xh, yl, yh;
+                unpack2(mul2(dx, dx), xl, xh);
+                unpack2(mul2(dy, dy), yl, yh);
+                const float d2[2] = {__fadd_rn(xl, yl), __fadd_rn(xh, yh)};  // b2DistanceSquared, no FMA
 #pragma unroll
-            for (int s = 0; s < APL; ++s) {
-                const float dx = q.x - o[s].x, dy = q.y - o[s].y;
-                const float d2 = dx * dx + dy * dy;  // b2DistanceSquared, no FMA
-                const bool take = (s * G == jb) ? ((d2 < best[s]) && notme) : (d2 < best[s]);
-                best[s] = take ? d2 : best[s];
-                bi[s] = take ? (jb + jj) : bi[s];
+                for (int s = 0; s < APL; ++s) {
+                    const bool take = (s * G == jb) ? ((d2[s] < best[s]) && notme) : (d2[s] < best[s]);
+                    best[s] = take ? d2[s] : best[s];
+                    bi[s] = take ? (jb + jj) : bi[s];
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int jb = 0; jb < G * APL; jb += G) {
+            const int jend = (N - jb) < G ? (N - jb) : G;
+#pragma unroll 4
+            for (int jj = 0; jj < jend; ++jj) {
+                const float2 q = pos[jb + jj];
+                const bool notme = jj != g.gl;
+#pragma unroll
+                for (int s = 0; s < APL; ++s) {
+                    const float dx = q.x - o[s].x, dy = q.y - o[s].y;
+                    const float d2 = dx * dx + dy * dy;  // b2DistanceSquared, no FMA
+                    const bool take = (s * G == jb) ? ((d2 < best[s]) && notme) : (d2 < best[s]);
+                    best[s] = take ? d2 : best[s];
+                    bi[s] = take ? (jb + jj) : bi[s];
+                }
             }
         }
     }
