@@ -398,4 +398,12 @@ extern "C" int macm_host_alloc(void** out, uint64_t bytes)
 
 extern "C" int macm_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? MACM_OK : MACM_E_CUDA; }
 
+extern "C" int macm_set_trace(macm_sim* sim, void* trace)
+{
+    if (!sim) return MACM_E_INVALID;
+    if (trace && !aligned(trace, 8)) return MACM_E_ALIGN;
+    sim->K.trace = (unsigned long long*)trace;
+    return MACM_OK;
+}
+
 extern "C" int64_t macm_launch_count(const macm_sim* sim) { return sim ? sim->launches : 0; }

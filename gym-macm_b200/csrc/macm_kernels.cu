@@ -48,8 +48,13 @@ struct Lay {
     static constexpr int NEW = ADJ + 8 * NC;
     static constexpr int ISLMIN = NEW;
     static constexpr int ANG = NEW + 4 * NC;
-    static constexpr int LABEL = NEW + 8 * NC;    // u8     [NC]  island seed of a body
-    static constexpr int STACK = LABEL + NC, LASTLVL = STACK + NC, ISLACT = LASTLVL + NC, ISLBAD = ISLACT + NC;
+    static constexpr int TMASK = NEW + 8 * NC;    // u32    [NC]  staged touching contacts (index < 32) of a body
+    static constexpr int LABEL = TMASK + 4 * NC;  // u32    [NC]  island seed (highest body index of the island)
+    static constexpr int STACK = LABEL + 4 * NC;  // u8     [NC]  DFS stack (intrusive next-pointers on the common path)
+    static constexpr int COMP = STACK + NC;       // u8     [NC]  seed body of the k-th island that has contacts
+    static constexpr int SOLVED = COMP + NC;      // u8     [NC]  position solver converged for the island seeded here
+    // dense piles only (more touching contacts than lanes, *_big below):
+    static constexpr int LASTLVL = SOLVED + NC, ISLACT = LASTLVL + NC, ISLBAD = ISLACT + NC;
     static constexpr int HEAD = ISLBAD + NC;      // u8     [NC]  newest touching contact of a body
     static constexpr int MISC = (HEAD + NC + 15) / 16 * 16;  // 4 x u32
     static constexpr int FIXED = MISC + 16;
@@ -77,8 +82,11 @@ struct EnvS {
     __device__ uint2* nw() const { return (uint2*)(base + Lay<NC>::NEW); }
     __device__ uint32_t* isl_min() const { return (uint32_t*)(base + Lay<NC>::ISLMIN); }
     __device__ float* ang() const { return (float*)(base + Lay<NC>::ANG); }
-    __device__ uint8_t* label() const { return base + Lay<NC>::LABEL; }
+    __device__ uint32_t* tmask() const { return (uint32_t*)(base + Lay<NC>::TMASK); }
+    __device__ uint32_t* label() const { return (uint32_t*)(base + Lay<NC>::LABEL); }
     __device__ uint8_t* stack() const { return base + Lay<NC>::STACK; }
+    __device__ uint8_t* comp() const { return base + Lay<NC>::COMP; }
+    __device__ uint8_t* solved() const { return base + Lay<NC>::SOLVED; }
     __device__ uint8_t* lastlvl() const { return base + Lay<NC>::LASTLVL; }
     __device__ uint8_t* isl_act() const { return base + Lay<NC>::ISLACT; }
     __device__ uint8_t* isl_bad() const { return base + Lay<NC>::ISLBAD; }
@@ -562,10 +570,13 @@ __device__ __noinline__ void solve_position_big(const Grp<G>& g, const EnvS<G * 
                                                 int nlev)
 {
     float2* pos = S.pos();
-    const uint8_t* label = S.label();
+    const uint32_t* label = S.label();
     uint8_t* isl_act = S.isl_act(); uint8_t* isl_bad = S.isl_bad();
     const uint32_t* t_ew = S.t_ew();
     const uint16_t* ordlvl = S.ordlvl();
+#pragma unroll
+    for (int s = 0; s < APL; ++s) { isl_act[g.gl + s * G] = 1; isl_bad[g.gl + s * G] = 0; }
+    g.sync();
     for (int it = 0; it < P.pos_iters; ++it) {
         for (int lev = 1; lev <= nlev; ++lev) {
             for (int k = g.gl; k < tc; k += G) {
@@ -594,6 +605,70 @@ __device__ __noinline__ void solve_position_big(const Grp<G>& g, const EnvS<G * 
         g.sync();
         if (!g.ballot(any_bad)) break;
     }
+#pragma unroll
+    for (int s = 0; s < APL; ++s) S.solved()[g.gl + s * G] = (P.pos_iters > 0) && !isl_act[g.gl + s * G];
+    g.sync();
+}
+
+// Islands of a dense pile (tc > G): Box2D's depth-first traversal replayed by one lane over
+// per-body edge lists (head-inserted in birth order, like b2ContactManager::AddPair builds them);
+// every contact gets its position in the island order and a level = 1 + max(level of the previous
+// contact of either body).  Contacts of one level share no body and run across lanes.
+template <int G, int APL>
+__device__ __noinline__ int islands_big(const Grp<G>& g, const EnvS<G * APL>& S, int tc)
+{
+    uint32_t* t_ew = S.t_ew();
+    uint16_t* ordlvl = S.ordlvl();
+    uint32_t* label = S.label();
+#pragma unroll
+    for (int s = 0; s < APL; ++s) { S.lastlvl()[g.gl + s * G] = 0; S.head()[g.gl + s * G] = EW_NONE; }
+    g.sync();
+    int L = 1;
+    if (g.gl == 0) {
+        uint8_t* stack = S.stack(); uint8_t* head = S.head(); uint8_t* lastlvl = S.lastlvl();
+        uint32_t rem_lo = 0u, rem_hi = 0u;   // bodies with a touching contact that are not in an island yet
+        for (int t = 0; t < tc; ++t) {
+            const uint32_t ew = t_ew[t];
+            const int a = EW_A(ew), b = EW_B(ew);
+            t_ew[t] = ew | ((uint32_t)head[a] << 12) | ((uint32_t)head[b] << 20);
+            head[a] = (uint8_t)t;
+            head[b] = (uint8_t)t;
+            if (a < 32) rem_lo |= 1u << a; else rem_hi |= 1u << (a - 32);
+            if (b < 32) rem_lo |= 1u << b; else rem_hi |= 1u << (b - 32);
+        }
+        int nord = 0;
+        while (rem_lo | rem_hi) {
+            const int seed = rem_hi ? (63 - __clz((int)rem_hi)) : (31 - __clz((int)rem_lo));
+            int sp = 0;
+            stack[sp++] = (uint8_t)seed;
+            if (seed < 32) rem_lo &= ~(1u << seed); else rem_hi &= ~(1u << (seed - 32));
+            while (sp > 0) {
+                const int b = stack[--sp];
+                label[b] = (uint32_t)seed;
+                for (int t = head[b]; t != EW_NONE;) {
+                    const uint32_t ew = t_ew[t];
+                    const int ta = EW_A(ew), tb = EW_B(ew);
+                    const int nx = (ta == b) ? EW_NA(ew) : EW_NB(ew);
+                    if (!(ew & EW_TAKEN)) {
+                        t_ew[t] = ew | EW_TAKEN;
+                        const int l = 1 + max((int)lastlvl[ta], (int)lastlvl[tb]);
+                        ordlvl[nord++] = (uint16_t)(t | (l << 8));
+                        lastlvl[ta] = (uint8_t)l;
+                        lastlvl[tb] = (uint8_t)l;
+                        L = max(L, l);
+                        const int other = (ta == b) ? tb : ta;
+                        const uint32_t ob = 1u << (other & 31);
+                        if (other < 32) { if (rem_lo & ob) { rem_lo &= ~ob; stack[sp++] = (uint8_t)other; } }
+                        else { if (rem_hi & ob) { rem_hi &= ~ob; stack[sp++] = (uint8_t)other; } }
+                    }
+                    t = nx;
+                }
+            }
+        }
+    }
+    L = g.shfl(L, 0);
+    g.sync();
+    return L;
 }
 
 // b2World::Step prologue of a world with new fixtures: FindNewContacts before Collide.  Runs on
@@ -634,6 +709,8 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
     const int slot_in_block = (threadIdx.x >> 5) * GPW + (threadIdx.x & 31) / G;
     const int env = blockIdx.x * (blockDim.x / 32) * GPW + slot_in_block;
     if (env >= P.E) return;  // whole group leaves together
+    unsigned long long tr_t0 = 0, tr_c0 = 0;
+    if (P.trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_t0)); tr_c0 = clock64(); }
     const int N = P.N;
     EnvS<NC> S;
     S.TC = P.TC;
@@ -641,8 +718,8 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
 
     float2* pos = S.pos(); float2* vel = S.vel(); float4* fat = S.fat();
     uint2* adj = S.adj();
-    uint8_t* label = S.label();
-    uint32_t* misc = S.misc();
+    uint32_t* label = S.label();
+    uint32_t* tmask = S.tmask();
 
     uint32_t* c_ab = P.c_ab + (size_t)env * P.C;
     float2* c_imp = P.c_imp + (size_t)env * P.C;
@@ -685,8 +762,8 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
         pos[i] = c[s];
         fat[i] = fatr[s];
         adj[i] = make_uint2(0u, 0u);
+        S.tmask()[i] = 0u;
     }
-    if (g.gl == 0) { misc[0] = 0; misc[1] = 0; misc[2] = 0; misc[3] = 0; }
 
     // ---- phase 1: actions -> angle, force (mvmnt.py:97-129 / combat.py:121-155), float64 like the reference
     bool attack[APL];
@@ -832,6 +909,7 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
     // destroy contacts whose fat AABBs stopped overlapping (or whose body was deactivated),
     // narrowphase the rest, compact in place (birth order is preserved), stage the touching ones
     int tc = 0;
+    bool multi = false;   // some body has two touching contacts: islands are more than pairs
     {
         float2* t_imp = S.t_imp();
         uint32_t* t_ew = S.t_ew();
@@ -869,10 +947,12 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
                     t_ew[tp] = (uint32_t)a | ((uint32_t)b << 6);
                     t_imp[tp] = make_float2(nI, tI);
                     t_slot[tp] = (uint16_t)p;
-                    // bodies with a touching contact (misc[0..1]); does any body carry two?
-                    const uint32_t oa = atomicOr(&misc[a >> 5], 1u << (a & 31));
-                    const uint32_t ob = atomicOr(&misc[b >> 5], 1u << (b & 31));
-                    dup |= ((oa >> (a & 31)) & 1) | ((ob >> (b & 31)) & 1);
+                    // the body's set of touching contacts; does any body carry two?
+                    if (tp < 32) {
+                        const uint32_t oa = atomicOr(&tmask[a], 1u << tp);
+                        const uint32_t ob = atomicOr(&tmask[b], 1u << tp);
+                        dup |= (oa | ob) != 0u;
+                    }
                 }
             }
             w += __popc(km);
@@ -880,7 +960,7 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
         }
         cnt = w;
         if (tc > P.TC) { overflow_t = true; tc = P.TC; }
-        if (g.ballot(dup)) { if (g.gl == 0) misc[2] = 1; }
+        multi = g.ballot(dup) != 0u;
     }
 
     // ---- phase 3: integrate velocities (b2Island::Solve, first loop) -------------------------
@@ -895,108 +975,52 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
             v[s].y *= P.damp;
         }
         vel[i] = v[s];
-        label[i] = (uint8_t)i;
-        S.isl_act()[i] = 1;
-        S.isl_bad()[i] = 0;
-        S.lastlvl()[i] = 0;
-        S.head()[i] = EW_NONE;
+        label[i] = (uint32_t)i;
+        // an island without contacts passes its first position iteration (minSeparation = 0)
+        S.solved()[i] = P.pos_iters > 0;
     }
     g.sync();
 
-    // ---- phase 4: islands (b2World::Solve DFS) -> solve order + levels -------------------------
-    // Box2D seeds islands from the body list (last-created body first), pops a stack, and walks
-    // each body's contact edges newest-first; contacts are solved in the order they are added.
-    // One lane replays exactly that over per-body edge lists (head-inserted in birth order, like
-    // b2ContactManager::AddPair does) and assigns each contact its level on the fly.
-    int nlev = tc > 0 ? 1 : 0;
-    const bool multi = misc[2] != 0;
-    if (tc > 0) {
-        uint32_t* t_ew = S.t_ew();
-        uint16_t* ordlvl = S.ordlvl();
-        if (!multi) {
-            // every body has at most one touching contact: contacts are independent, any order
-            // gives the same bits; islands are the pairs themselves (seed = higher index)
-            for (int k = g.gl; k < tc; k += G) {
-                ordlvl[k] = (uint16_t)(k | (1 << 8));
-                const uint32_t ew = t_ew[k];
-                label[EW_A(ew)] = (uint8_t)EW_B(ew);
-                label[EW_B(ew)] = (uint8_t)EW_B(ew);
-            }
-        } else {
-            int L = 1;
-            if (g.gl == 0) {
-                uint8_t* stack = S.stack(); uint8_t* head = S.head(); uint8_t* lastlvl = S.lastlvl();
-                for (int t = 0; t < tc; ++t) {
-                    const uint32_t ew = t_ew[t];
-                    const int a = EW_A(ew), b = EW_B(ew);
-                    t_ew[t] = ew | ((uint32_t)head[a] << 12) | ((uint32_t)head[b] << 20);
-                    head[a] = (uint8_t)t;
-                    head[b] = (uint8_t)t;
-                }
-                // bodies with a touching contact that are not in an island yet
-                uint32_t rem_lo = misc[0], rem_hi = misc[1];
-                int nord = 0;
-                while (rem_lo | rem_hi) {
-                    const int seed = rem_hi ? (63 - __clz((int)rem_hi)) : (31 - __clz((int)rem_lo));
-                    int sp = 0;
-                    stack[sp++] = (uint8_t)seed;
-                    if (seed < 32) rem_lo &= ~(1u << seed); else rem_hi &= ~(1u << (seed - 32));
-                    while (sp > 0) {
-                        const int b = stack[--sp];
-                        label[b] = (uint8_t)seed;
-                        for (int t = head[b]; t != EW_NONE;) {
-                            const uint32_t ew = t_ew[t];
-                            const int ta = EW_A(ew), tb = EW_B(ew);
-                            const int nx = (ta == b) ? EW_NA(ew) : EW_NB(ew);
-                            if (!(ew & EW_TAKEN)) {
-                                t_ew[t] = ew | EW_TAKEN;
-                                const int l = 1 + max((int)lastlvl[ta], (int)lastlvl[tb]);
-                                ordlvl[nord++] = (uint16_t)(t | (l << 8));
-                                lastlvl[ta] = (uint8_t)l;
-                                lastlvl[tb] = (uint8_t)l;
-                                L = max(L, l);
-                                const int other = (ta == b) ? tb : ta;
-                                const uint32_t ob = 1u << (other & 31);
-                                if (other < 32) { if (rem_lo & ob) { rem_lo &= ~ob; stack[sp++] = (uint8_t)other; } }
-                                else { if (rem_hi & ob) { rem_hi &= ~ob; stack[sp++] = (uint8_t)other; } }
-                            }
-                            t = nx;
-                        }
-                    }
-                }
-            }
-            nlev = g.shfl(L, 0);
-        }
-        g.sync();
-    }
-
-    // ---- phase 5: contact solver, velocity part -------------------------------------------------
-    // Order position k is owned by lane k.  With tc <= G (all but dense piles) a lane keeps its
-    // contact in registers for the whole solve; otherwise the generic out-of-line solver runs.
+    // ---- phase 4: islands (b2World::Solve) ---------------------------------------------------------
+    // Box2D seeds islands from the body list (last-created body first), pops a stack, walks each
+    // body's contact edges newest-first and solves an island's contacts in the order it added them.
+    // Islands share no body, so each one is replayed and solved by ONE lane, sequentially, in exactly
+    // that order -- no ordering between islands is needed and no barrier inside the solver.
+    //   * no body with two touching contacts (the usual case): islands are the pairs themselves,
+    //     contact k lives in the registers of lane k for the whole solve;
+    //   * otherwise (tc <= G): label propagation finds each island's seed (its highest body index),
+    //     the k-th seed goes to lane k, which runs the DFS over the bodies' touching-contact sets
+    //     (bit t = staged contact t, highest = newest) and threads the contacts into a list;
+    //   * dense piles (tc > G): one lane replays the DFS for the whole world and the contacts are
+    //     level-scheduled across lanes (islands_big / solve_*_big, out of line).
     const bool big = tc > G;
     const bool has = !big && g.gl < tc;
-    int ka = 0, kb = 0, klv = 0, kt = 0, kisl = 0;
+    int nlev = 0;
+    int ka = 0, kb = 0;
     float knx = 1.0f, kny = 0.0f, knI = 0.0f, ktI = 0.0f;
+    int ohead = EW_NONE, oseed = 0;     // multi: first contact of this lane's island, its seed body
     // inv_dt0 == 0 on a world's first step -> dtRatio 0
     const float ratio = (es.x == 0) ? 0.0f : P.dt_ratio;
+
+    // ---- phase 5: contact solver, velocity part -------------------------------------------------
     if (big) {
+        nlev = islands_big<G, APL>(g, S, tc);
         solve_velocity_big<G, APL>(g, S, P, tc, nlev, ratio, c_imp);
     } else if (tc > 0) {
         const float mass_n = P.normal_mass, mass_t = P.normal_mass;
+        uint32_t* t_ew = S.t_ew();
         // b2ContactSolver ctor + InitializeVelocityConstraints: world manifold at the
         // pre-integration positions, impulses scaled by dtRatio
         if (has) {
-            const int ol = S.ordlvl()[g.gl];
-            kt = ol & 0xff; klv = ol >> 8;
-            const uint32_t ew = S.t_ew()[kt];
-            ka = EW_A(ew); kb = EW_B(ew); kisl = label[ka];
+            const uint32_t ew = t_ew[g.gl];
+            ka = EW_A(ew); kb = EW_B(ew);
             const float2 pa = pos[ka], pb = pos[kb];
             const float dx = pb.x - pa.x, dy = pb.y - pa.y;
             // b2DistanceSquared(pointA, pointB) is (A - B).(A - B); squares are sign-blind
             if ((dx * dx + dy * dy) > B2_EPSILON * B2_EPSILON) { knx = dx; kny = dy; b2normalize(knx, kny); }
-            if (P.warm_starting) { const float2 im = S.t_imp()[kt]; knI = ratio * im.x; ktI = ratio * im.y; }
+            if (P.warm_starting) { const float2 im = S.t_imp()[g.gl]; knI = ratio * im.x; ktI = ratio * im.y; }
         }
-        if (nlev == 1) {
+        if (!multi) {
             // independent contacts: warm start + all iterations without leaving registers
             if (has) {
                 float2 va = vel[ka], vb = vel[kb];
@@ -1004,23 +1028,93 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
                 for (int it = 0; it < P.vel_iters; ++it)
                     solve_velocity(knx, kny, P.friction, mass_n, mass_t, P.inv_mass, knI, ktI, va, vb);
                 vel[ka] = va; vel[kb] = vb;
+                label[ka] = (uint32_t)kb;   // the pair's island is seeded by its higher index
+                oseed = kb;
+                // StoreImpulses -> manifold (next step's warm start)
+                c_imp[S.t_slot()[g.gl]] = make_float2(knI, ktI);
             }
             g.sync();
         } else {
-            for (int it = -1; it < P.vel_iters; ++it) {   // it == -1: WarmStart, in order
-                for (int lev = 1; lev <= nlev; ++lev) {
-                    if (has && klv == lev) {
-                        float2 va = vel[ka], vb = vel[kb];
-                        if (it < 0) warm_start(knx, kny, knI, ktI, P.inv_mass, va, vb);
-                        else solve_velocity(knx, kny, P.friction, mass_n, mass_t, P.inv_mass, knI, ktI, va, vb);
-                        vel[ka] = va; vel[kb] = vb;
+            float2* t_n = S.t_n(); float2* t_imp = S.t_imp();
+            if (has) { t_n[g.gl] = make_float2(knx, kny); t_imp[g.gl] = make_float2(knI, ktI); }
+            // island seeds: propagate the highest body index along touching contacts
+            bool changed;
+            do {
+                changed = false;
+                if (has) {
+                    const uint32_t la = label[ka], lb = label[kb];
+                    if (la != lb) {
+                        changed = true;
+                        const uint32_t m = la > lb ? la : lb;
+                        atomicMax(&label[ka], m);
+                        atomicMax(&label[kb], m);
                     }
-                    g.sync();
                 }
+                g.sync();
+            } while (g.ballot(changed));
+            // the k-th seed (ascending) goes to lane k
+            {
+                int ncomp = 0;
+#pragma unroll
+                for (int s = 0; s < APL; ++s) {
+                    const int i = g.gl + s * G;
+                    const bool seed = tmask[i] != 0u && label[i] == (uint32_t)i;
+                    const unsigned sm = g.ballot(seed);
+                    if (seed) S.comp()[ncomp + __popc(sm & g.below())] = (uint8_t)i;
+                    ncomp += __popc(sm);
+                }
+                nlev = ncomp;
+                g.sync();
+                if (g.gl < ncomp) {
+                    oseed = S.comp()[g.gl];
+                    uint8_t* nxt = S.stack();
+                    uint32_t taken = 0u, vis_lo = 0u, vis_hi = 0u;
+                    int top = oseed, otail = EW_NONE;
+                    uint32_t otail_ew = 0u;
+                    nxt[oseed] = EW_NONE;
+                    if (oseed < 32) vis_lo = 1u << oseed; else vis_hi = 1u << (oseed - 32);
+                    while (top != EW_NONE) {
+                        const int b = top;
+                        top = nxt[b];
+                        for (uint32_t m = tmask[b] & ~taken; m;) {
+                            const int t = 31 - __clz((int)m);   // newest edge first
+                            m &= ~(1u << t);
+                            taken |= 1u << t;
+                            const uint32_t ew = t_ew[t] & 0xfffu;
+                            if (otail == EW_NONE) ohead = t; else t_ew[otail] = otail_ew | ((uint32_t)t << 12);
+                            otail = t; otail_ew = ew;
+                            const int other = (EW_A(ew) == b) ? EW_B(ew) : EW_A(ew);
+                            const uint32_t ob = 1u << (other & 31);
+                            const bool seen = ((other < 32 ? vis_lo : vis_hi) & ob) != 0u;
+                            if (!seen) {
+                                if (other < 32) vis_lo |= ob; else vis_hi |= ob;
+                                nxt[other] = (uint8_t)top;
+                                top = other;
+                            }
+                        }
+                    }
+                    t_ew[otail] = otail_ew | ((uint32_t)EW_NONE << 12);
+                    // b2ContactSolver::WarmStart, then the velocity iterations, in island order
+                    for (int it = -1; it < P.vel_iters; ++it) {
+                        for (int t = ohead; t != EW_NONE;) {
+                            const uint32_t ew = t_ew[t];
+                            const float2 n = t_n[t];
+                            float2 im = t_imp[t];
+                            const int a = EW_A(ew), b = EW_B(ew);
+                            float2 va = vel[a], vb = vel[b];
+                            if (it < 0) warm_start(n.x, n.y, im.x, im.y, P.inv_mass, va, vb);
+                            else solve_velocity(n.x, n.y, P.friction, mass_n, mass_t, P.inv_mass, im.x, im.y, va, vb);
+                            vel[a] = va; vel[b] = vb;
+                            t_imp[t] = im;
+                            t = EW_NA(ew);
+                        }
+                    }
+                }
+                g.sync();
+                // StoreImpulses -> manifold (next step's warm start)
+                if (has) c_imp[S.t_slot()[g.gl]] = t_imp[g.gl];
             }
         }
-        // StoreImpulses -> manifold (next step's warm start)
-        if (has) c_imp[S.t_slot()[kt]] = make_float2(knI, ktI);
     }
 
     // ---- phase 6: integrate positions ------------------------------------------------------------
@@ -1045,43 +1139,45 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
     for (int s = 0; s < APL; ++s) pos[g.gl + s * G] = c[s];
     g.sync();
 
-    // ---- phase 7: contact solver, position part (per-island early exit) ---------------------------
-    {
-        uint8_t* isl_act = S.isl_act(); uint8_t* isl_bad = S.isl_bad();
-        if (big) {
-            solve_position_big<G, APL>(g, S, P, tc, nlev);
+    // ---- phase 7: contact solver, position part (each island stops as soon as it is solved) -------
+    if (big) {
+        solve_position_big<G, APL>(g, S, P, tc, nlev);
 #pragma unroll
-            for (int s = 0; s < APL; ++s) c[s] = pos[g.gl + s * G];
-        } else if (tc > 0) {
-            for (int it = 0; it < P.pos_iters; ++it) {
-                for (int lev = 1; lev <= nlev; ++lev) {
-                    if (has && klv == lev && isl_act[kisl]) {
-                        float2 ca = pos[ka], cb = pos[kb];
-                        const float sep = solve_position(P.radius, P.k_sum, P.inv_mass, ca, cb);
-                        pos[ka] = ca; pos[kb] = cb;
-                        // island not solved while min(0, separations) < -3 * linearSlop
-                        if (!(b2min(0.0f, sep) >= -3.0f * B2_LINEAR_SLOP)) isl_bad[kisl] = 1;
-                    }
-                    g.sync();
+        for (int s = 0; s < APL; ++s) c[s] = pos[g.gl + s * G];
+    } else if (tc > 0) {
+        if (!multi) {
+            if (has) {
+                float2 ca = pos[ka], cb = pos[kb];
+                bool ok = false;
+                for (int it = 0; it < P.pos_iters && !ok; ++it) {
+                    const float sep = solve_position(P.radius, P.k_sum, P.inv_mass, ca, cb);
+                    // solved once min(0, separations) >= -3 * linearSlop
+                    ok = b2min(0.0f, sep) >= -3.0f * B2_LINEAR_SLOP;
                 }
-                bool any_bad = false;
-#pragma unroll
-                for (int s = 0; s < APL; ++s) {
-                    const int i = g.gl + s * G;
-                    const uint8_t bad = isl_bad[i];
-                    isl_act[i] = bad;
-                    isl_bad[i] = 0;
-                    any_bad |= bad != 0;
-                }
-                g.sync();
-                if (!g.ballot(any_bad)) break;
+                pos[ka] = ca; pos[kb] = cb;
+                S.solved()[oseed] = ok;
             }
-#pragma unroll
-            for (int s = 0; s < APL; ++s) c[s] = pos[g.gl + s * G];
-        } else if (P.pos_iters > 0) {
-#pragma unroll
-            for (int s = 0; s < APL; ++s) isl_act[g.gl + s * G] = 0;
+        } else if (ohead != EW_NONE) {
+            const uint32_t* t_ew = S.t_ew();
+            bool ok = false;
+            for (int it = 0; it < P.pos_iters && !ok; ++it) {
+                float min_sep = 0.0f;
+                for (int t = ohead; t != EW_NONE;) {
+                    const uint32_t ew = t_ew[t];
+                    const int a = EW_A(ew), b = EW_B(ew);
+                    float2 ca = pos[a], cb = pos[b];
+                    const float sep = solve_position(P.radius, P.k_sum, P.inv_mass, ca, cb);
+                    pos[a] = ca; pos[b] = cb;
+                    min_sep = b2min(min_sep, sep);
+                    t = EW_NA(ew);
+                }
+                ok = min_sep >= -3.0f * B2_LINEAR_SLOP;
+            }
+            S.solved()[oseed] = ok;
         }
+        g.sync();
+#pragma unroll
+        for (int s = 0; s < APL; ++s) c[s] = pos[g.gl + s * G];
     }
 
     // ---- phase 8: sleeping (b2Island::Solve tail) --------------------------------------------------
@@ -1097,7 +1193,6 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
         }
         if (g.ballot(cand)) {
             uint32_t* isl_min = S.isl_min();
-            uint8_t* isl_act = S.isl_act();
 #pragma unroll
             for (int s = 0; s < APL; ++s) isl_min[g.gl + s * G] = 0x7f7fffffu;  // b2_maxFloat
             g.sync();
@@ -1108,7 +1203,7 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
 #pragma unroll
             for (int s = 0; s < APL; ++s) {
                 const int isl = label[g.gl + s * G];
-                const bool solved = (P.pos_iters > 0) && !isl_act[isl];
+                const bool solved = S.solved()[isl] != 0;
                 if (now_alive[s] && __uint_as_float(isl_min[isl]) >= B2_TIME_TO_SLEEP && solved) {
                     // SetAwake(false); the next ApplyForce(wake=True) wakes the body again
                     slp[s] = 0.0f; v[s] = make_float2(0.0f, 0.0f);
@@ -1206,6 +1301,14 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
         tdm_observe<G, APL>(g, S, P, env, alive);
     } else {
         flock_observe<G, APL>(g, S, P, env, ang);
+    }
+    if (P.trace && g.gl == 0) {   // macm_set_trace: per-env timing record
+        unsigned long long t1, smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        asm volatile("{.reg .u32 t; mov.u32 t, %%smid; cvt.u64.u32 %0, t;}" : "=l"(smid));
+        unsigned long long* tr = P.trace + (size_t)env * 4;
+        tr[0] = tr_t0; tr[1] = t1; tr[2] = clock64() - tr_c0;
+        tr[3] = smid | ((unsigned long long)tc << 16) | ((unsigned long long)nlev << 32) | ((unsigned long long)multi << 48);
     }
 }
 

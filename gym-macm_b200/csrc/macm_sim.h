@@ -48,6 +48,7 @@ struct SimConst {
     float4* tdm; const uint8_t* team;
     // outputs
     float* obs; int* nn_idx; float* rewards; uint8_t* collided; uint8_t* done;
+    unsigned long long* trace;  // [E,4] per-env timing record (macm_set_trace), or null
 };
 
 struct LaunchCfg {

@@ -59,7 +59,7 @@ EXPORTS = ("macm_abi_version", "macm_strerror", "macm_last_cuda_error", "macm_pa
            "macm_destroy", "macm_get_buffer_sizes", "macm_get_launch_info", "macm_bind", "macm_reset",
            "macm_sample_reset", "macm_step", "macm_observe", "macm_bot_actions", "macm_step_host", "macm_step_host_async", "macm_host_sync",
            "macm_host_alloc",
-           "macm_host_free", "macm_launch_count")
+           "macm_host_free", "macm_launch_count", "macm_set_trace")
 
 
 class MacmError(RuntimeError):
@@ -101,6 +101,7 @@ def lib():
         L.macm_host_free.argtypes = [vp]
         L.macm_launch_count.restype = C.c_int64
         L.macm_launch_count.argtypes = [vp]
+        L.macm_set_trace.argtypes = [vp, vp]
         if L.macm_abi_version() != 1:
             raise MacmError("libmacm.so ABI version mismatch")
         _lib = L

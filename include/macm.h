@@ -222,6 +222,11 @@ int macm_host_free(void* p);
 /* Number of kernels this handle has launched so far. */
 int64_t macm_launch_count(const macm_sim* sim);
 
+/* Profiling hook (no reference counterpart): when `trace` is a device buffer of n_envs x 4 uint64,
+ * every step launch records per env {%globaltimer at entry (ns), %globaltimer at exit (ns), SM cycles
+ * spent, smid | touching<<16 | levels<<32 | multi<<48}.  NULL switches it off (the default). */
+int macm_set_trace(macm_sim* sim, void* trace);
+
 #ifdef __cplusplus
 }
 #endif
