@@ -25,8 +25,19 @@
 
 #include "macm_sim.h"
 
-#ifndef MACM_MIN_BLOCKS
-#define MACM_MIN_BLOCKS 7
+// Launch shapes: 128-thread blocks, 7 per SM (72 registers); or, when the whole batch is one wave of
+// one-env-per-warp groups, one 896-thread block per SM.  (Measured on B200, profiles/README.md: the
+// warp scheduler favours the warps of the oldest resident block, so with seven small blocks the last
+// block's warps only get the issue slots the others leave and an env with large islands in that
+// block sets the kernel time; warps of one block are served evenly.)
+#define MACM_WIDE_THREADS 896
+
+// Phase stamps for profiles/phase_trace.py (a separate build with -DMACM_PHASE_TRACE; the trace
+// buffer then holds 16 words per env: SM clock at the end of each phase, relative to the start).
+#ifdef MACM_PHASE_TRACE
+#define PHASE_STAMP(k) do { g.sync(); if (P.trace && g.gl == 0) P.trace[(size_t)env * 16 + (k)] = clock64() - tr_c0; } while (0)
+#else
+#define PHASE_STAMP(k) do { } while (0)
 #endif
 
 namespace {
@@ -48,7 +59,8 @@ struct Lay {
     static constexpr int NEW = ADJ + 8 * NC;
     static constexpr int ISLMIN = NEW;
     static constexpr int ANG = NEW + 4 * NC;
-    static constexpr int TMASK = NEW + 8 * NC;    // u32    [NC]  staged touching contacts (index < 32) of a body
+    static constexpr int TGT = NEW + 8 * NC;      // float2 [NC]  the agent's target (Flock), staged with the state
+    static constexpr int TMASK = TGT + 8 * NC;    // u32    [NC]  staged touching contacts (index < 32) of a body
     static constexpr int LABEL = TMASK + 4 * NC;  // u32    [NC]  island seed (highest body index of the island)
     static constexpr int STACK = LABEL + 4 * NC;  // u8     [NC]  DFS stack (intrusive next-pointers on the common path)
     static constexpr int COMP = STACK + NC;       // u8     [NC]  seed body of the k-th island that has contacts
@@ -82,6 +94,7 @@ struct EnvS {
     __device__ uint2* nw() const { return (uint2*)(base + Lay<NC>::NEW); }
     __device__ uint32_t* isl_min() const { return (uint32_t*)(base + Lay<NC>::ISLMIN); }
     __device__ float* ang() const { return (float*)(base + Lay<NC>::ANG); }
+    __device__ float2* tgt() const { return (float2*)(base + Lay<NC>::TGT); }
     __device__ uint32_t* tmask() const { return (uint32_t*)(base + Lay<NC>::TMASK); }
     __device__ uint32_t* label() const { return (uint32_t*)(base + Lay<NC>::LABEL); }
     __device__ uint8_t* stack() const { return base + Lay<NC>::STACK; }
@@ -401,8 +414,7 @@ __device__ void flock_observe(const Grp<G>& g, const EnvS<G * APL>& S, const Sim
         o[s] = pos[i];
         best[s] = __int_as_float(0x7f800000);
         bi[s] = -1;
-        // issued before the search so that the latency hides behind it
-        tg[s] = P.targets[(size_t)env * P.T + P.target_idx[i < N ? i : 0]];
+        tg[s] = S.tgt()[i];
     }
     // nearest other agent: strict '<' over ascending j keeps the lowest index on ties (mvmnt.py:194).
     // Slot s only has to skip itself while j runs through its own 32-block.
@@ -698,7 +710,7 @@ __device__ __noinline__ int fresh_world_contacts(const Grp<G>& g, const EnvS<G *
 // the step kernel
 // ------------------------------------------------------------------------------------------
 template <int G, int APL, int KIND>
-__global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const __grid_constant__ SimConst P,
+__global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const __grid_constant__ SimConst P,
                                                         const void* __restrict__ actions)
 {
     constexpr int NC = G * APL;
@@ -707,10 +719,9 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Grp<G> g;
     const int slot_in_block = (threadIdx.x >> 5) * GPW + (threadIdx.x & 31) / G;
-    const int env = blockIdx.x * (blockDim.x / 32) * GPW + slot_in_block;
-    if (env >= P.E) return;  // whole group leaves together
+    const int slot = blockIdx.x * (blockDim.x / 32) * GPW + slot_in_block;
+    if (slot >= P.E) return;  // whole group leaves together
     unsigned long long tr_t0 = 0, tr_c0 = 0;
-    if (P.trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_t0)); tr_c0 = clock64(); }
     const int N = P.N;
     EnvS<NC> S;
     S.TC = P.TC;
@@ -721,6 +732,13 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
     uint32_t* label = S.label();
     uint32_t* tmask = S.tmask();
 
+    // Programmatic dependent launch: this grid may have been scheduled while the previous kernel of
+    // the stream was still draining (its blocks take the SM slots as they free up).  Nothing above
+    // touches global memory; wait here for the predecessor's writes, then let the next launch in.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (P.trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_t0)); tr_c0 = clock64(); }
+    const int env = slot;
     uint32_t* c_ab = P.c_ab + (size_t)env * P.C;
     float2* c_imp = P.c_imp + (size_t)env * P.C;
 
@@ -729,9 +747,14 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
     float ang[APL], slp[APL];
     float4 fatr[APL];
     bool valid[APL];
+    uint32_t act_raw[APL];
     uint2 alive = make_uint2(0u, 0u);   // bodies that are active (have a proxy) during this step
     const int4 es = P.env_state[env];
     int cnt = P.c_cnt[env];
+    // first chunk of the contact list, fetched together with the state (one HBM round trip less)
+    uint32_t pre_ab = 0u;
+    float2 pre_imp = make_float2(0.0f, 0.0f);
+    if (g.gl < P.C) { pre_ab = c_ab[g.gl]; pre_imp = c_imp[g.gl]; }
     // TDM per-agent host state (combat.Agent): health, cool-downs (steps left), alive, hits taken
     float health[APL];
     int cd_atk[APL], cd_mov[APL], hits[APL];
@@ -763,8 +786,13 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
         fat[i] = fatr[s];
         adj[i] = make_uint2(0u, 0u);
         S.tmask()[i] = 0u;
+        if (!TDM) S.tgt()[i] = P.targets[(size_t)env * P.T + P.target_idx[valid[s] ? i : 0]];
+        // discrete action word, fetched with the state
+        act_raw[s] = 0u;
+        if ((TDM || P.action_mode == MACM_ACTION_DISCRETE) && valid[s]) act_raw[s] = reinterpret_cast<const uint32_t*>(actions)[gi];
     }
 
+    PHASE_STAMP(0);
     // ---- phase 1: actions -> angle, force (mvmnt.py:97-129 / combat.py:121-155), float64 like the reference
     bool attack[APL];
 #pragma unroll
@@ -775,7 +803,7 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
         if (!was_alive[s]) continue;
         const size_t gi = (size_t)env * N + i;
         if (TDM || P.action_mode == MACM_ACTION_DISCRETE) {
-            const uint32_t act = reinterpret_cast<const uint32_t*>(actions)[gi];
+            const uint32_t act = act_raw[s];
             const int a0 = (int)(act & 0xff) - 1, a1 = (int)((act >> 8) & 0xff) - 1, a2 = (int)((act >> 16) & 0xff) - 1;
             // body.angle = body.angle + (a2-1) * rotation_speed * (1/hz)   -> SetTransform rounds to fp32
             float af = (float)((double)ang[s] + (double)a2 * P.rot_step);
@@ -830,6 +858,7 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
     }
     g.sync();
 
+    PHASE_STAMP(1);
     // ---- phase 1b (TDM): closest-hit ray casts, health, deaths (combat.py:141-165, cm_framework.py:56-86)
     bool now_alive[APL];
 #pragma unroll
@@ -902,6 +931,7 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
 
     bool overflow_c = false, overflow_t = false;
 
+    PHASE_STAMP(2);
     // ---- phase 2a: new fixtures -> FindNewContacts before Collide (b2World::Step prologue) ----
     if (es.y & MACM_ENV_FRESH) cnt = fresh_world_contacts<G, APL>(g, S, P, alive, cnt, c_ab, c_imp, overflow_c);
 
@@ -921,7 +951,10 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
             const bool in = k < cnt;
             uint32_t ab = 0;
             float2 imp = make_float2(0.0f, 0.0f);
-            if (in) { ab = c_ab[k]; imp = c_imp[k]; }
+            if (in) {
+                if (base == 0 && !(es.y & MACM_ENV_FRESH)) { ab = pre_ab; imp = pre_imp; }
+                else { ab = c_ab[k]; imp = c_imp[k]; }
+            }
             g.sync();  // every lane holds its record before any lane compacts over it
             const int a = ab & 0xff, b = (ab >> 8) & 0xff;
             bool keep = in && aabb_overlap(fat[a], fat[b]);
@@ -963,6 +996,7 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
         multi = g.ballot(dup) != 0u;
     }
 
+    PHASE_STAMP(3);
     // ---- phase 3: integrate velocities (b2Island::Solve, first loop) -------------------------
 #pragma unroll
     for (int s = 0; s < APL; ++s) {
@@ -981,6 +1015,7 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
     }
     g.sync();
 
+    PHASE_STAMP(4);
     // ---- phase 4: islands (b2World::Solve) ---------------------------------------------------------
     // Box2D seeds islands from the body list (last-created body first), pops a stack, walks each
     // body's contact edges newest-first and solves an island's contacts in the order it added them.
@@ -1117,6 +1152,7 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
         }
     }
 
+    PHASE_STAMP(5);
     // ---- phase 6: integrate positions ------------------------------------------------------------
     float2 c0[APL];
 #pragma unroll
@@ -1139,6 +1175,7 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
     for (int s = 0; s < APL; ++s) pos[g.gl + s * G] = c[s];
     g.sync();
 
+    PHASE_STAMP(6);
     // ---- phase 7: contact solver, position part (each island stops as soon as it is solved) -------
     if (big) {
         solve_position_big<G, APL>(g, S, P, tc, nlev);
@@ -1180,6 +1217,7 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
         for (int s = 0; s < APL; ++s) c[s] = pos[g.gl + s * G];
     }
 
+    PHASE_STAMP(7);
     // ---- phase 8: sleeping (b2Island::Solve tail) --------------------------------------------------
     {
         bool cand = false;
@@ -1212,6 +1250,7 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
         }
     }
 
+    PHASE_STAMP(8);
     // ---- phase 9: SynchronizeFixtures -> b2DynamicTree::MoveProxy -----------------------------------
     uint2 moved = make_uint2(0u, 0u);
 #pragma unroll
@@ -1236,9 +1275,11 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
     }
     g.sync();
 
+    PHASE_STAMP(9);
     // ---- phase 10: FindNewContacts ------------------------------------------------------------------
     if (moved.x | moved.y) cnt = find_new_contacts<G, APL>(g, S, P, moved, alive, cnt, c_ab, c_imp, overflow_c);
 
+    PHASE_STAMP(10);
     // ---- phase 11: rewards (mvmnt.py:160-179), time/done (mvmnt.py:134-136) ---------------------------
     const int step = es.x + 1;
     bool done = step >= P.done_step;
@@ -1266,7 +1307,7 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
         if (TDM) {
             rew = (now_alive[s] && col) ? -1.0f : 0.0f;
         } else if (!col) {
-            const float2 tg = P.targets[(size_t)env * P.T + P.target_idx[i]];
+            const float2 tg = S.tgt()[i];
             const float dx = tg.x - c[s].x, dy = tg.y - c[s].y;
             const float d2 = dx * dx + dy * dy;
             if (P.reward_mode == MACM_REWARD_LINEAR) rew = (-sqrtf(d2) / 35.0f) + 1.0f;
@@ -1284,6 +1325,7 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
             S.ang()[i] = ang[s];
         }
     }
+
     {
         const bool oc = g.ballot(overflow_c) != 0, ot = g.ballot(overflow_t) != 0;
         if (g.gl == 0) {
@@ -1295,6 +1337,7 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
         }
     }
 
+    PHASE_STAMP(11);
     // ---- phase 13: observations (mvmnt.py:181-222 / combat.py:206-227) ----------------------------
     if (TDM) {
         g.sync();
@@ -1302,14 +1345,20 @@ __global__ void __launch_bounds__(128, MACM_MIN_BLOCKS) macm_step_kernel(const _
     } else {
         flock_observe<G, APL>(g, S, P, env, ang);
     }
+    PHASE_STAMP(12);
+#ifndef MACM_PHASE_TRACE
     if (P.trace && g.gl == 0) {   // macm_set_trace: per-env timing record
         unsigned long long t1, smid;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
         asm volatile("{.reg .u32 t; mov.u32 t, %%smid; cvt.u64.u32 %0, t;}" : "=l"(smid));
         unsigned long long* tr = P.trace + (size_t)env * 4;
         tr[0] = tr_t0; tr[1] = t1; tr[2] = clock64() - tr_c0;
-        tr[3] = smid | ((unsigned long long)tc << 16) | ((unsigned long long)nlev << 32) | ((unsigned long long)multi << 48);
+        tr[3] = smid | ((unsigned long long)tc << 16) | ((unsigned long long)nlev << 32) | ((unsigned long long)multi << 48) |
+                ((unsigned long long)(slot & 0x7fff) << 49);
     }
+#else
+    if (P.trace && g.gl == 0) P.trace[(size_t)env * 16 + 15] = (unsigned long long)tc | ((unsigned long long)multi << 16);
+#endif
 }
 
 // get_obs() alone
@@ -1337,6 +1386,7 @@ __global__ void __launch_bounds__(128) macm_observe_kernel(const __grid_constant
         ang[s] = P.angsleep[gi].x;
         S.pos()[i] = ok ? make_float2(pv.x, pv.y) : make_float2(3.0e30f, 3.0e30f);
         S.ang()[i] = ang[s];
+        if (KIND != MACM_ENV_TDM) S.tgt()[i] = P.targets[(size_t)env * P.T + P.target_idx[ok ? i : 0]];
         bool al = ok;
         if (KIND == MACM_ENV_TDM) al = ok && (__float_as_int(P.tdm[gi].w) & 1);
         const unsigned bm = g.ballot(al);
@@ -1375,9 +1425,23 @@ __global__ void macm_reset_kernel(const __grid_constant__ SimConst P)
 template <int G, int APL, int KIND>
 cudaError_t launch_one(const SimConst& P, const LaunchCfg& cfg, const void* actions, cudaStream_t s, bool observe_only)
 {
-    if (observe_only) macm_observe_kernel<G, APL, KIND><<<cfg.blocks, cfg.threads, cfg.smem_bytes, s>>>(P);
-    else macm_step_kernel<G, APL, KIND><<<cfg.blocks, cfg.threads, cfg.smem_bytes, s>>>(P, actions);
-    return cudaGetLastError();
+    if (observe_only) {
+        macm_observe_kernel<G, APL, KIND><<<cfg.obs_blocks, 128, cfg.obs_smem_bytes, s>>>(P);
+        return cudaGetLastError();
+    }
+    // the step kernel is launched with programmatic stream serialization: it may become resident
+    // before its predecessor in the stream has finished and waits in griddepcontrol.wait
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)cfg.blocks);
+    lc.blockDim = dim3((unsigned)cfg.threads);
+    lc.dynamicSmemBytes = (size_t)cfg.smem_bytes;
+    lc.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    return cudaLaunchKernelEx(&lc, macm_step_kernel<G, APL, KIND>, P, actions);
 }
 
 template <int G, int APL, int KIND>
@@ -1387,7 +1451,7 @@ cudaError_t prepare_one(const LaunchCfg& cfg, int* blocks_per_sm)
                                          cfg.smem_bytes);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(macm_observe_kernel<G, APL, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             cfg.smem_bytes);
+                             cfg.obs_smem_bytes);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, macm_step_kernel<G, APL, KIND>, cfg.threads,
                                                          cfg.smem_bytes);
@@ -1405,11 +1469,15 @@ static void pick_shape(int N, int* G, int* APL)
     else { *G = 32; *APL = 2; }
 }
 
-cudaError_t macm_launch_cfg(const SimConst& P, LaunchCfg* cfg)
+cudaError_t macm_launch_cfg(const SimConst& P, int sm_count, LaunchCfg* cfg)
 {
     pick_shape(P.N, &cfg->G, &cfg->APL);
+    const int gpw = 32 / cfg->G;
     cfg->threads = 128;
-    cfg->envs_per_block = (cfg->threads / 32) * (32 / cfg->G);
+    // one wave of one-env-per-warp groups: a block per SM, envs dealt heavy-first inside it
+    const int wide_warps = MACM_WIDE_THREADS / 32;
+    if (gpw == 1 && sm_count > 0 && (P.E + wide_warps - 1) / wide_warps <= sm_count && P.E > 4) cfg->threads = MACM_WIDE_THREADS;
+    cfg->envs_per_block = (cfg->threads / 32) * gpw;
     cfg->blocks = (P.E + cfg->envs_per_block - 1) / cfg->envs_per_block;
     const int NC = cfg->G * cfg->APL;
     int per_env = 0;
@@ -1420,7 +1488,15 @@ cudaError_t macm_launch_cfg(const SimConst& P, LaunchCfg* cfg)
         case 32: per_env = Lay<32>::bytes(P.TC); break;
         default: per_env = Lay<64>::bytes(P.TC); break;
     }
+    cfg->per_env_bytes = per_env;
+    if (per_env * cfg->envs_per_block > 227 * 1024) {   // fall back to narrow blocks
+        cfg->threads = 128;
+        cfg->envs_per_block = 4 * gpw;
+        cfg->blocks = (P.E + cfg->envs_per_block - 1) / cfg->envs_per_block;
+    }
     cfg->smem_bytes = per_env * cfg->envs_per_block;
+    cfg->obs_blocks = (P.E + 4 * gpw - 1) / (4 * gpw);
+    cfg->obs_smem_bytes = per_env * 4 * gpw;
     return cfg->smem_bytes <= 227 * 1024 ? cudaSuccess : cudaErrorInvalidConfiguration;
 }
 

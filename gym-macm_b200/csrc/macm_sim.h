@@ -52,11 +52,13 @@ struct SimConst {
 };
 
 struct LaunchCfg {
-    int G, APL, envs_per_block, threads, blocks, smem_bytes;
+    int G, APL, envs_per_block, threads, blocks, smem_bytes;   // the step kernel
+    int per_env_bytes;                                          // shared memory of one env
+    int obs_blocks, obs_smem_bytes;                             // get_obs alone: always 128-thread blocks
 };
 
 // implemented in macm_kernels.cu
-cudaError_t macm_launch_cfg(const SimConst& P, LaunchCfg* cfg);
+cudaError_t macm_launch_cfg(const SimConst& P, int sm_count, LaunchCfg* cfg);
 cudaError_t macm_prepare_kernels(const SimConst& P, const LaunchCfg& cfg, int* blocks_per_sm);
 cudaError_t macm_launch_step(const SimConst& P, const LaunchCfg& cfg, const void* actions, cudaStream_t s);
 cudaError_t macm_launch_observe(const SimConst& P, const LaunchCfg& cfg, cudaStream_t s);

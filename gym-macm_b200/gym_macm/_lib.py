@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmacm.so")
+LIB_PATH = os.environ.get("MACM_LIB") or os.path.join(_HERE, "libmacm.so")   # MACM_LIB: instrumented builds (profiles/)
 
 FLOCK, TDM = 0, 1
 REWARD = {"binary": 0, "linear": 1}

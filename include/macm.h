@@ -224,7 +224,7 @@ int64_t macm_launch_count(const macm_sim* sim);
 
 /* Profiling hook (no reference counterpart): when `trace` is a device buffer of n_envs x 4 uint64,
  * every step launch records per env {%globaltimer at entry (ns), %globaltimer at exit (ns), SM cycles
- * spent, smid | touching<<16 | levels<<32 | multi<<48}.  NULL switches it off (the default). */
+ * spent, smid | touching<<16 | islands<<32 | multi<<48 | slot<<49}.  NULL switches it off (the default). */
 int macm_set_trace(macm_sim* sim, void* trace);
 
 #ifdef __cplusplus
