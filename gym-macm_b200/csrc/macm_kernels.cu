@@ -1071,84 +1071,93 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
             g.sync();
         } else {
             float2* t_n = S.t_n(); float2* t_imp = S.t_imp();
-            if (has) { t_n[g.gl] = make_float2(knx, kny); t_imp[g.gl] = make_float2(knI, ktI); }
-            // island seeds: propagate the highest body index along touching contacts
-            bool changed;
-            do {
-                changed = false;
-                if (has) {
-                    const uint32_t la = label[ka], lb = label[kb];
-                    if (la != lb) {
-                        changed = true;
-                        const uint32_t m = la > lb ? la : lb;
-                        atomicMax(&label[ka], m);
-                        atomicMax(&label[kb], m);
-                    }
-                }
-                g.sync();
-            } while (g.ballot(changed));
-            // the k-th seed (ascending) goes to lane k
-            {
-                int ncomp = 0;
-#pragma unroll
-                for (int s = 0; s < APL; ++s) {
-                    const int i = g.gl + s * G;
-                    const bool seed = tmask[i] != 0u && label[i] == (uint32_t)i;
-                    const unsigned sm = g.ballot(seed);
-                    if (seed) S.comp()[ncomp + __popc(sm & g.below())] = (uint8_t)i;
-                    ncomp += __popc(sm);
-                }
-                nlev = ncomp;
-                g.sync();
-                if (g.gl < ncomp) {
-                    oseed = S.comp()[g.gl];
-                    uint8_t* nxt = S.stack();
-                    uint32_t taken = 0u, vis_lo = 0u, vis_hi = 0u;
-                    int top = oseed, otail = EW_NONE;
-                    uint32_t otail_ew = 0u;
-                    nxt[oseed] = EW_NONE;
-                    if (oseed < 32) vis_lo = 1u << oseed; else vis_hi = 1u << (oseed - 32);
-                    while (top != EW_NONE) {
-                        const int b = top;
-                        top = nxt[b];
-                        for (uint32_t m = tmask[b] & ~taken; m;) {
-                            const int t = 31 - __clz((int)m);   // newest edge first
-                            m &= ~(1u << t);
-                            taken |= 1u << t;
-                            const uint32_t ew = t_ew[t] & 0xfffu;
-                            if (otail == EW_NONE) ohead = t; else t_ew[otail] = otail_ew | ((uint32_t)t << 12);
-                            otail = t; otail_ew = ew;
-                            const int other = (EW_A(ew) == b) ? EW_B(ew) : EW_A(ew);
-                            const uint32_t ob = 1u << (other & 31);
-                            const bool seen = ((other < 32 ? vis_lo : vis_hi) & ob) != 0u;
-                            if (!seen) {
-                                if (other < 32) vis_lo |= ob; else vis_hi |= ob;
-                                nxt[other] = (uint8_t)top;
-                                top = other;
-                            }
-                        }
-                    }
-                    t_ew[otail] = otail_ew | ((uint32_t)EW_NONE << 12);
-                    // b2ContactSolver::WarmStart, then the velocity iterations, in island order
-                    for (int it = -1; it < P.vel_iters; ++it) {
-                        for (int t = ohead; t != EW_NONE;) {
-                            const uint32_t ew = t_ew[t];
-                            const float2 n = t_n[t];
-                            float2 im = t_imp[t];
-                            const int a = EW_A(ew), b = EW_B(ew);
-                            float2 va = vel[a], vb = vel[b];
-                            if (it < 0) warm_start(n.x, n.y, im.x, im.y, P.inv_mass, va, vb);
-                            else solve_velocity(n.x, n.y, P.friction, mass_n, mass_t, P.inv_mass, im.x, im.y, va, vb);
-                            vel[a] = va; vel[b] = vb;
-                            t_imp[t] = im;
-                            t = EW_NA(ew);
-                        }
-                    }
-                }
-                g.sync();
-                // StoreImpulses -> manifold (next step's warm start)
-                if (has) c_imp[S.t_slot()[g.gl]] = t_imp[g.gl];
+            // Islands = connected sets of touching contacts.  Contact t lives in lane t; the contacts
+            // next to it are the touching-contact sets of its two bodies.  The sets are closed under
+            // "shares a body" with shuffles (islands are a few contacts: one or two rounds), together
+            // with the highest body index of the island, which is Box2D's seed for it.
+            uint32_t cset = 0u;
+            int seed = 0;
+            if (has) {
+                t_n[g.gl] = make_float2(knx, kny);
+                t_imp[g.gl] = make_float2(knI, ktI);
+                cset = tmask[ka] | tmask[kb];
+                seed = kb;   // a < b
             }
+            for (;;) {
+                uint32_t acc = cset;
+                int top = seed;
+                uint32_t todo = cset & ~(1u << g.gl);
+                while (g.ballot(todo != 0u)) {
+                    const int u = todo ? (__ffs((int)todo) - 1) : g.gl;
+                    const uint32_t cu = (uint32_t)g.shfl((int)cset, u);
+                    const int su = g.shfl(seed, u);
+                    acc |= cu;
+                    top = max(top, su);
+                    todo &= todo - 1u;
+                }
+                const bool changed = acc != cset || top != seed;
+                cset = acc; seed = top;
+                if (!g.ballot(changed)) break;
+            }
+            nlev = 0;
+            if (has) { label[ka] = (uint32_t)seed; label[kb] = (uint32_t)seed; }
+            g.sync();
+            // the lane of an island's first contact replays Box2D's DFS for it and then solves it
+            if (has && (__ffs((int)cset) - 1) == g.gl) {
+                oseed = seed;
+                uint8_t* nxt = S.stack();
+                uint32_t taken = 0u, vis_lo = 0u, vis_hi = 0u;
+                int top = oseed, otail = EW_NONE;
+                uint32_t otail_ew = 0u;
+                nxt[oseed] = EW_NONE;
+                if (oseed < 32) vis_lo = 1u << oseed; else vis_hi = 1u << (oseed - 32);
+                while (top != EW_NONE) {
+                    const int b = top;
+                    top = nxt[b];
+                    for (uint32_t m = tmask[b] & ~taken; m;) {
+                        const int t = 31 - __clz((int)m);   // newest edge first
+                        m &= ~(1u << t);
+                        taken |= 1u << t;
+                        const uint32_t ew = t_ew[t] & 0xfffu;
+                        if (otail == EW_NONE) ohead = t; else t_ew[otail] = otail_ew | ((uint32_t)t << 12);
+                        otail = t; otail_ew = ew;
+                        const int other = (EW_A(ew) == b) ? EW_B(ew) : EW_A(ew);
+                        const uint32_t ob = 1u << (other & 31);
+                        const bool seen = ((other < 32 ? vis_lo : vis_hi) & ob) != 0u;
+                        if (!seen) {
+                            if (other < 32) vis_lo |= ob; else vis_hi |= ob;
+                            nxt[other] = (uint8_t)top;
+                            top = other;
+                        }
+                    }
+                }
+                t_ew[otail] = otail_ew | ((uint32_t)EW_NONE << 12);
+                // b2ContactSolver::WarmStart, then the velocity iterations, in island order.  The next
+                // contact's record is fetched while the current one is being solved.
+                const uint32_t ew_head = t_ew[ohead];
+                const float2 n_head = t_n[ohead];
+                for (int it = -1; it < P.vel_iters; ++it) {
+                    int t = ohead;
+                    uint32_t ew = ew_head;
+                    float2 n = n_head, im = t_imp[t];
+                    for (;;) {
+                        const int a = EW_A(ew), b = EW_B(ew), tn = EW_NA(ew);
+                        float2 va = vel[a], vb = vel[b];
+                        uint32_t ew2 = 0u;
+                        float2 n2 = make_float2(0.0f, 0.0f), im2 = n2;
+                        if (tn != EW_NONE) { ew2 = t_ew[tn]; n2 = t_n[tn]; im2 = t_imp[tn]; }
+                        if (it < 0) warm_start(n.x, n.y, im.x, im.y, P.inv_mass, va, vb);
+                        else solve_velocity(n.x, n.y, P.friction, mass_n, mass_t, P.inv_mass, im.x, im.y, va, vb);
+                        vel[a] = va; vel[b] = vb;
+                        t_imp[t] = im;
+                        if (tn == EW_NONE) break;
+                        t = tn; ew = ew2; n = n2; im = im2;
+                    }
+                }
+            }
+            g.sync();
+            // StoreImpulses -> manifold (next step's warm start)
+            if (has) c_imp[S.t_slot()[g.gl]] = t_imp[g.gl];
         }
     }
 
@@ -1196,17 +1205,21 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
             }
         } else if (ohead != EW_NONE) {
             const uint32_t* t_ew = S.t_ew();
+            const uint32_t ew_head = t_ew[ohead];
             bool ok = false;
             for (int it = 0; it < P.pos_iters && !ok; ++it) {
                 float min_sep = 0.0f;
-                for (int t = ohead; t != EW_NONE;) {
-                    const uint32_t ew = t_ew[t];
-                    const int a = EW_A(ew), b = EW_B(ew);
+                uint32_t ew = ew_head;
+                for (;;) {
+                    const int a = EW_A(ew), b = EW_B(ew), tn = EW_NA(ew);
                     float2 ca = pos[a], cb = pos[b];
+                    uint32_t ew2 = 0u;
+                    if (tn != EW_NONE) ew2 = t_ew[tn];
                     const float sep = solve_position(P.radius, P.k_sum, P.inv_mass, ca, cb);
                     pos[a] = ca; pos[b] = cb;
                     min_sep = b2min(min_sep, sep);
-                    t = EW_NA(ew);
+                    if (tn == EW_NONE) break;
+                    ew = ew2;
                 }
                 ok = min_sep >= -3.0f * B2_LINEAR_SLOP;
             }
