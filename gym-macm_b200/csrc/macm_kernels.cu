@@ -386,6 +386,123 @@ __device__ int find_new_contacts(const Grp<G>& g, const EnvS<G * APL>& S, const 
 }
 
 // ------------------------------------------------------------------------------------------
+// Nearest other agent for the two agents of a lane (N in 33..64; agents gl and gl + 32).
+//
+// The select/compare pipe is the scarce one on this path (16 lanes per sub-partition against 32 for
+// the FMA pipes), so the search spends its work on the FMA side: squared distances in packed fp32x2
+// (lo half = the lane's first agent, hi half = its second) and, per block of four candidates, one
+// 3-input min + min + compare + select per agent -- the running minimum and the BLOCK it came from.
+// The index inside the block is recovered afterwards by recomputing four distances.
+//
+// Positions are staged as P4[j] = (x_j, x_{j+32}, y_j, y_{j+32}), j = 0..31, twice in a row, so that
+//   * the lane's own half (agents of the same 32-block) is read at P4[gl + r], r = 1..31: every
+//     other agent of the block exactly once, never itself, no index arithmetic, no self test;
+//   * the other half is read at P4[j], j = 0..31 (broadcast), against the lane's agents swapped.
+// The reference keeps the lowest index among equal minima (strict '<' in ascending order,
+// mvmnt.py:194).  The broadcast half is visited in ascending order, so there the first block wins
+// and the lowest index inside it is taken; the rotated half is not, so an exact tie between a
+// block's minimum and the running minimum raises a flag and that agent is re-scanned in order
+// (nn_rescan: about one agent-step in 10^5).
+// ------------------------------------------------------------------------------------------
+template <int NC>
+__device__ __noinline__ float2 nn_rescan(const float2* pos, float2 o, int self)
+{
+    float best = __int_as_float(0x7f800000);
+    int bi = -1;
+    for (int j = 0; j < NC; ++j) {
+        const float2 q = pos[j];
+        const float dx = q.x - o.x, dy = q.y - o.y;
+        const float d2 = dx * dx + dy * dy;
+        if (j != self && d2 < best) { best = d2; bi = j; }
+    }
+    return make_float2(best, __int_as_float(bi));
+}
+
+#define NN_D2(q, OX, OY, dl, dh)                                                             \
+    {                                                                                        \
+        const f32x2 dx_ = sub2(pack2((q).x, (q).y), OX), dy_ = sub2(pack2((q).z, (q).w), OY); \
+        float xl_, xh_, yl_, yh_;                                                            \
+        unpack2(mul2(dx_, dx_), xl_, xh_);                                                   \
+        unpack2(mul2(dy_, dy_), yl_, yh_);                                                   \
+        dl = __fadd_rn(xl_, yl_); dh = __fadd_rn(xh_, yh_);   /* b2DistanceSquared, no FMA */ \
+    }
+
+template <int G>
+__device__ __forceinline__ void nn_search_64(const Grp<G>& g, const EnvS<2 * G>& S, float2 o0, float2 o1,
+                                             float& best0, int& bi0, float& best1, int& bi1)
+{
+    static_assert(G == 32, "two agents per lane means 32 lanes per env");
+    const float2* pos = S.pos();
+    float4* P4 = reinterpret_cast<float4*>(S.fat());   // the fat AABBs are dead by now
+    g.sync();
+    P4[g.gl] = P4[g.gl + 32] = make_float4(o0.x, o1.x, o0.y, o1.y);
+    g.sync();
+    const float BIG = 3.4028234664e38f;   // every real squared distance is below it; padding agents give +inf
+    const f32x2 ox = pack2(o0.x, o1.x), oy = pack2(o0.y, o1.y);      // own half: lo = agent gl, hi = agent gl + 32
+    const f32x2 oxs = pack2(o1.x, o0.x), oys = pack2(o1.y, o0.y);    // other half: lo = agent gl + 32 against A_j, hi = agent gl against B_j
+    float bo0 = BIG, bo1 = BIG, bc0 = BIG, bc1 = BIG;   // running minima: own half (agent 0, agent 1), other half
+    int ko0 = 0, ko1 = 0, kc0 = 0, kc1 = 0;              // first candidate of the block of the minimum
+    // smallest |block minimum - running minimum| seen: exactly 0 <=> an exact draw (the subtraction goes
+    // to the FMA pipe, the |.| min is one op on the other)
+    float tz0 = BIG, tz1 = BIG;
+    const float4* own = P4 + g.gl + 1;
+    // (the loop counter doubles as the block id: one add and one compare per block)
+#pragma unroll 1
+    for (int b = 0; b < 28; b += 4) {
+        float dl[4], dh[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float4 q = own[b + k]; NN_D2(q, ox, oy, dl[k], dh[k]); }
+        const float ml = fminf(fminf(fminf(dl[0], dl[1]), dl[2]), dl[3]), mh = fminf(fminf(fminf(dh[0], dh[1]), dh[2]), dh[3]);
+        tz0 = fminf(tz0, fabsf(ml - bo0)); tz1 = fminf(tz1, fabsf(mh - bo1));
+        const bool pl = ml < bo0, ph = mh < bo1;
+        bo0 = fminf(bo0, ml); bo1 = fminf(bo1, mh);
+        ko0 = pl ? b : ko0; ko1 = ph ? b : ko1;
+    }
+    {   // r = 29, 30, 31
+        float dl[3], dh[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { const float4 q = own[28 + k]; NN_D2(q, ox, oy, dl[k], dh[k]); }
+        const float ml = fminf(fminf(dl[0], dl[1]), dl[2]), mh = fminf(fminf(dh[0], dh[1]), dh[2]);
+        tz0 = fminf(tz0, fabsf(ml - bo0)); tz1 = fminf(tz1, fabsf(mh - bo1));
+        const bool pl = ml < bo0, ph = mh < bo1;
+        bo0 = fminf(bo0, ml); bo1 = fminf(bo1, mh);
+        ko0 = pl ? 28 : ko0; ko1 = ph ? 28 : ko1;
+    }
+    const bool tie0 = tz0 == 0.0f, tie1 = tz1 == 0.0f;
+#pragma unroll 1
+    for (int b = 0; b < 32; b += 4) {
+        float dl[4], dh[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float4 q = P4[b + k]; NN_D2(q, oxs, oys, dl[k], dh[k]); }
+        // lo: agent gl + 32 against A_j ; hi: agent gl against B_j
+        const float ml = fminf(fminf(fminf(dl[0], dl[1]), dl[2]), dl[3]), mh = fminf(fminf(fminf(dh[0], dh[1]), dh[2]), dh[3]);
+        const bool pl = ml < bc1, ph = mh < bc0;
+        bc1 = fminf(bc1, ml); bc0 = fminf(bc0, mh);
+        kc1 = pl ? b : kc1; kc0 = ph ? b : kc0;
+    }
+    // agent gl: its own half holds the lower indices, so it wins an exact draw; agent gl + 32: the other half does
+    const bool own0 = bo0 <= bc0, own1 = bo1 < bc1;
+    best0 = own0 ? bo0 : bc0;
+    best1 = own1 ? bo1 : bc1;
+    bi0 = 64; bi1 = 64;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r0 = 1 + ko0 + k, r1 = 1 + ko1 + k;
+        const int c0 = own0 ? ((g.gl + r0) & 31) : (32 + kc0 + k);
+        const int c1 = own1 ? (32 + ((g.gl + r1) & 31)) : (kc1 + k);
+        const bool in0 = !own0 || r0 < 32, in1 = !own1 || r1 < 32;
+        const float2 q0 = pos[c0], q1 = pos[c1];
+        const float ax = q0.x - o0.x, ay = q0.y - o0.y, bx = q1.x - o1.x, by = q1.y - o1.y;
+        const float d0 = ax * ax + ay * ay, d1 = bx * bx + by * by;
+        if (in0 && d0 == best0) bi0 = min(bi0, c0);
+        if (in1 && d1 == best1) bi1 = min(bi1, c1);
+    }
+    // an exact draw in the rotated half (or nothing found: every other agent infinitely far): in order, from scratch
+    if ((own0 && tie0) || bi0 == 64) { const float2 r = nn_rescan<64>(pos, o0, g.gl); best0 = r.x; bi0 = __float_as_int(r.y); }
+    if ((own1 && tie1) || bi1 == 64) { const float2 r = nn_rescan<64>(pos, o1, g.gl + 32); best1 = r.x; bi1 = __float_as_int(r.y); }
+}
+
+// ------------------------------------------------------------------------------------------
 // observation pass for the agents a lane owns (Flock.get_obs, mvmnt.py:181-222)
 // ------------------------------------------------------------------------------------------
 // cartesian variant of the observation record (coord == "cartesian", mvmnt.py:202-203,215-216); cold
@@ -414,39 +531,11 @@ __device__ void flock_observe(const Grp<G>& g, const EnvS<G * APL>& S, const Sim
         o[s] = pos[i];
         best[s] = __int_as_float(0x7f800000);
         bi[s] = -1;
-        tg[s] = S.tgt()[i];
     }
     // nearest other agent: strict '<' over ascending j keeps the lowest index on ties (mvmnt.py:194).
     // Slot s only has to skip itself while j runs through its own 32-block.
-    if (APL == 2) {
-        // both agents of a lane against candidate j in packed fp32x2: positions are re-staged as
-        // (x, x, y, y) over the fat-AABB region, which is dead by now
-        float4* pos4 = reinterpret_cast<float4*>(S.fat());
-        g.sync();
-#pragma unroll
-        for (int s = 0; s < APL; ++s) pos4[g.gl + s * G] = make_float4(o[s].x, o[s].x, o[s].y, o[s].y);
-        g.sync();
-        const f32x2 ox = pack2(o[0].x, o[APL - 1].x), oy = pack2(o[0].y, o[APL - 1].y);
-#pragma unroll
-        for (int jb = 0; jb < G * APL; jb += G) {
-            const int jend = (N - jb) < G ? (N - jb) : G;
-#pragma unroll 4
-            for (int jj = 0; jj < jend; ++jj) {
-                const float4 q = pos4[jb + jj];
-                const bool notme = jj != g.gl;
-                const f32x2 dx = sub2(pack2(q.x, q.y), ox), dy = sub2(pack2(q.z, q.w), oy);
-                float xl, xh, yl, yh;
-                unpack2(mul2(dx, dx), xl, xh);
-                unpack2(mul2(dy, dy), yl, yh);
-                const float d2[2] = {__fadd_rn(xl, yl), __fadd_rn(xh, yh)};  // b2DistanceSquared, no FMA
-#pragma unroll
-                for (int s = 0; s < APL; ++s) {
-                    const bool take = (s * G == jb) ? ((d2[s] < best[s]) && notme) : (d2[s] < best[s]);
-                    best[s] = take ? d2[s] : best[s];
-                    bi[s] = take ? (jb + jj) : bi[s];
-                }
-            }
-        }
+    if constexpr (APL == 2) {
+        nn_search_64<G>(g, S, o[0], o[APL - 1], best[0], bi[0], best[APL - 1], bi[APL - 1]);
     } else {
 #pragma unroll
         for (int jb = 0; jb < G * APL; jb += G) {
@@ -470,6 +559,7 @@ __device__ void flock_observe(const Grp<G>& g, const EnvS<G * APL>& S, const Sim
     for (int s = 0; s < APL; ++s) {
         const int i = g.gl + s * G;
         if (i >= N) continue;
+        tg[s] = S.tgt()[i];
         const size_t gi = (size_t)env * N + i;
         float nn_d = __int_as_float(0x7f800000), nn_t = 0.0f;
         if (bi[s] >= 0) {
