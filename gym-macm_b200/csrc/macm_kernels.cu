@@ -159,6 +159,14 @@ __device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mo
 __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 
+// pull `bytes` starting at p towards L2, one 128-byte line per lane of the group
+template <int G>
+__device__ __forceinline__ void prefetch_l2(int gl, const void* p, int bytes)
+{
+    for (int off = gl * 128; off < bytes; off += G * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)p + off));
+}
+
 // b2TestOverlap(b2AABB, b2AABB): d1 = b.lo - a.hi, d2 = a.lo - b.hi; overlap iff no component > 0.
 // With IEEE gradual underflow (no -ftz) x - y > 0 <=> x > y, so the subtractions are not needed.
 __device__ __forceinline__ bool aabb_overlap(const float4 a, const float4 b)
@@ -823,8 +831,27 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
     uint32_t* tmask = S.tmask();
 
     // Programmatic dependent launch: this grid may have been scheduled while the previous kernel of
-    // the stream was still draining (its blocks take the SM slots as they free up).  Nothing above
-    // touches global memory; wait here for the predecessor's writes, then let the next launch in.
+    // the stream was still draining (its blocks take the SM slots as they free up).  No value is read
+    // from global memory before the wait; the env's lines are only pulled towards L2 (the coherence
+    // point, so a line the predecessor is still writing cannot go stale there), which takes the HBM
+    // latency of the state off the critical path whenever there is a predecessor to overlap with.
+    {
+        const int env_ = slot;
+        const size_t a0 = (size_t)env_ * P.N;
+        prefetch_l2<G>(g.gl, P.posvel + a0, P.N * 16);
+        prefetch_l2<G>(g.gl, P.fat + a0, P.N * 16);
+        prefetch_l2<G>(g.gl, P.angsleep + a0, P.N * 8);
+        prefetch_l2<G>(g.gl, (const char*)actions + a0 * (P.action_mode == MACM_ACTION_DISCRETE || TDM ? 4 : 8),
+                       P.N * (P.action_mode == MACM_ACTION_DISCRETE || TDM ? 4 : 8));
+        if (TDM) prefetch_l2<G>(g.gl, P.tdm + a0, P.N * 16);
+        prefetch_l2<G>(g.gl, P.c_ab + (size_t)env_ * P.C, 128);
+        prefetch_l2<G>(g.gl, P.c_imp + (size_t)env_ * P.C, 256);
+        if (g.gl == 0) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(P.env_state + env_));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(P.c_cnt + env_));
+            if (!TDM) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.targets + (size_t)env_ * P.T));
+        }
+    }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (P.trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_t0)); tr_c0 = clock64(); }
