@@ -22,6 +22,7 @@
 // The reference's host arithmetic is Python float64 (angle update, sin/cos, force); that part is
 // done in fp64 here and rounded to fp32 exactly where pybox2d's SWIG layer rounds.
 #include <float.h>
+#include <stdlib.h>
 
 #include "macm_sim.h"
 
@@ -1219,6 +1220,10 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
             nlev = 0;
             if (has) { label[ka] = (uint32_t)seed; label[kb] = (uint32_t)seed; }
             g.sync();
+#ifdef MACM_PHASE_TRACE
+            if (P.trace && g.gl == 0) P.trace[(size_t)env * 16 + 13] = clock64() - tr_c0;
+            unsigned long long dfs_done = 0;
+#endif
             // the lane of an island's first contact replays Box2D's DFS for it and then solves it
             if (has && (__ffs((int)cset) - 1) == g.gl) {
                 oseed = seed;
@@ -1249,6 +1254,9 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
                     }
                 }
                 t_ew[otail] = otail_ew | ((uint32_t)EW_NONE << 12);
+#ifdef MACM_PHASE_TRACE
+                dfs_done = clock64() - tr_c0;
+#endif
                 // b2ContactSolver::WarmStart, then the velocity iterations, in island order.  The next
                 // contact's record is fetched while the current one is being solved.
                 const uint32_t ew_head = t_ew[ohead];
@@ -1273,6 +1281,12 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
                 }
             }
             g.sync();
+#ifdef MACM_PHASE_TRACE
+            {
+                const unsigned lo = __reduce_max_sync(g.mask, (unsigned)dfs_done);
+                if (P.trace && g.gl == 0) P.trace[(size_t)env * 16 + 14] = lo;
+            }
+#endif
             // StoreImpulses -> manifold (next step's warm start)
             if (has) c_imp[S.t_slot()[g.gl]] = t_imp[g.gl];
         }
@@ -1607,6 +1621,10 @@ cudaError_t macm_launch_cfg(const SimConst& P, int sm_count, LaunchCfg* cfg)
     // one wave of one-env-per-warp groups: a block per SM, envs dealt heavy-first inside it
     const int wide_warps = MACM_WIDE_THREADS / 32;
     if (gpw == 1 && sm_count > 0 && (P.E + wide_warps - 1) / wide_warps <= sm_count && P.E > 4) cfg->threads = MACM_WIDE_THREADS;
+    if (const char* e = getenv("MACM_BLOCK_THREADS")) {   // experiments (profiles/README.md): 128 or 896
+        const int t = atoi(e);
+        if (t == 128 || (t == MACM_WIDE_THREADS && gpw == 1)) cfg->threads = t;
+    }
     cfg->envs_per_block = (cfg->threads / 32) * gpw;
     cfg->blocks = (P.E + cfg->envs_per_block - 1) / cfg->envs_per_block;
     const int NC = cfg->G * cfg->APL;

@@ -39,13 +39,14 @@ if __name__ == "__main__":
     sim = gym_macm.BatchedFlock(E, n_agents=[N], reward_mode="linear", device=dev, seed=1234)
     g = torch.Generator(device=dev)
     g.manual_seed(99)
-    acts = torch.zeros((16, E, N, 4), dtype=torch.uint8, device=dev)
-    acts[..., :3] = torch.randint(0, 3, (16, E, N, 3), generator=g, device=dev, dtype=torch.uint8)
+    POOL = 61   # like bench.py: fresh random actions every step
+    acts = torch.zeros((POOL, E, N, 4), dtype=torch.uint8, device=dev)
+    acts[..., :3] = torch.randint(0, 3, (POOL, E, N, 3), generator=g, device=dev, dtype=torch.uint8)
     for k in range(settle):
-        sim.engine.step(acts[k % 16])
+        sim.engine.step(acts[k % POOL])
     tr = torch.zeros((E, 16), dtype=torch.int64, device=dev)
     _lib.check(_lib.lib().macm_set_trace(sim.engine._h, C.c_void_p(tr.data_ptr())))
-    sim.engine.step(acts[3])
+    sim.engine.step(acts[settle % POOL])
     torch.cuda.synchronize()
     t = tr.cpu().numpy()
     names = ["0 load", "1 actions", "1b tdm", "2a+2 collide", "3 integrate v", "4+5 islands, velocity solver", "6 integrate x",
@@ -59,3 +60,11 @@ if __name__ == "__main__":
     for k, nm in enumerate(names):
         print("%-32s %9.0f %9.0f %9.0f %9.0f" % ((nm,) + tuple(d[s_, k].mean() if s_.any() else 0 for s_ in sel)))
     print("%-32s %9.0f %9.0f %9.0f %9.0f" % (("total",) + tuple(t[s_, 12].mean() if s_.any() else 0 for s_ in sel)))
+    m = multi == 1
+    if m.any():
+        print("multi envs, inside 4+5: contact init + island closure %.0f, DFS %.0f, velocity lists %.0f (cycles, mean)" % (
+            (t[m, 13] - t[m, 4]).mean(), (t[m, 14] - t[m, 13]).mean(), (t[m, 5] - t[m, 14]).mean()))
+        for k in sorted(set(tc[m]))[:8]:
+            s_ = m & (tc == k)
+            print("   tc=%d: envs %d  closure %.0f  DFS %.0f  lists %.0f  position %.0f" % (k, s_.sum(), (t[s_, 13] - t[s_, 4]).mean(),
+                  (t[s_, 14] - t[s_, 13]).mean(), (t[s_, 5] - t[s_, 14]).mean(), d[s_, 7].mean()))
