@@ -169,6 +169,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=60)
     ap.add_argument("--policy", default="random", choices=["random", "flock"])
     ap.add_argument("--settle", type=int, default=64, help="untimed steps per batch after the random spawn")
+    ap.add_argument("--max-touching", type=int, default=0, help="experiment: capacity of the touching-contact stage (0 = default)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -191,7 +192,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     E, N, ROT = args.envs, N_AGENTS, args.rot
 
-    sims = [gym_macm.BatchedFlock(E, n_agents=[N], reward_mode="linear", device=dev, seed=1234 + 1000 * rank + r)
+    extra = {"max_touching": args.max_touching} if args.max_touching else {}
+    sims = [gym_macm.BatchedFlock(E, n_agents=[N], reward_mode="linear", device=dev, seed=1234 + 1000 * rank + r, **extra)
             for r in range(ROT)]
     # U{0,1,2}^3 per agent-step, pre-generated on the device (a pool cycled through)
     g = torch.Generator(device=dev)
