@@ -167,6 +167,7 @@ def main():
     ap.add_argument("--gather", action="store_true", help="NCCL all-gather of obs+rewards every step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--e2e-steps", type=int, default=60)
+    ap.add_argument("--e2e-depth", type=int, default=3, help="independent batches in flight on the host-buffer path")
     ap.add_argument("--policy", default="random", choices=["random", "flock"])
     ap.add_argument("--settle", type=int, default=64, help="untimed steps per batch after the random spawn")
     ap.add_argument("--max-touching", type=int, default=0, help="experiment: capacity of the touching-contact stage (0 = default)")
@@ -263,29 +264,29 @@ def main():
 
     # ---- end to end through the host-buffer entry point (macm_step_host) --------------------
     e2e = None
-    # two batches in ping-pong (the usual double-buffered rollout): while one batch's observations
-    # travel to the host, the other batch steps.  Every step still pays its own H2D of actions and
-    # D2H of obs + rewards + done inside the timed region.
-    pp = sims[:2]
+    # DEPTH batches in rotation (the usual double/triple-buffered rollout): while one batch's
+    # observations travel to the host, the others step.  Every step still pays its own H2D of actions
+    # (from pinned host memory, where the host policy left them) and its own D2H of obs + rewards +
+    # done inside the timed region, and the host reads a result before it issues the batch's next step.
+    DEPTH = max(1, min(args.e2e_depth, ROT))
+    pp = sims[:DEPTH]
     want = ("obs", "rewards", "done")
     pin = pp[0].engine.pinned()
-    host_actions = [acts[i].cpu() for i in range(4)]
+    host_actions = [acts[i].cpu().pin_memory() for i in range(4)]
     for s_ in pp:
         for k in range(3):
-            s_.engine.pinned()["actions"].copy_(host_actions[k % 4])
-            s_.engine.step_host(s_.engine.pinned()["actions"], want=want)
+            s_.engine.step_host(host_actions[k % 4], want=want)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     checksum = 0.0
     te = time.perf_counter()
     for k in range(args.e2e_steps):
-        cur = pp[k % 2].engine
-        if k >= 2:
+        cur = pp[k % DEPTH].engine
+        if k >= DEPTH:
             cur.host_sync()                                   # results of this batch's previous step
             checksum += float(cur.pinned()["rewards"][0, 0])  # the host reads them
-        cur.pinned()["actions"].copy_(host_actions[k % 4])    # this step's actions, written by the host
-        cur.step_host(cur.pinned()["actions"], want=want, wait=False)
+        cur.step_host(host_actions[k % 4], want=want, wait=False)
     for s_ in pp:
         s_.engine.host_sync()
     el = time.perf_counter() - te
@@ -297,8 +298,8 @@ def main():
     d2h = int(sum(pin[k].numel() * pin[k].element_size() for k in ("obs", "rewards", "done")))
     e2e = {"value": world * E * N * args.e2e_steps / el, "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
-           "path": "macm_step_host_async/macm_host_sync on two batches in ping-pong: pinned host actions -> device, "
-                   "step kernel, obs+rewards+done -> pinned host"}
+           "path": "macm_step_host_async/macm_host_sync on %d batches in rotation: pinned host actions -> device, "
+                   "step kernel, obs+rewards+done -> pinned host" % DEPTH}
 
     if rank == 0:
         cpu = None

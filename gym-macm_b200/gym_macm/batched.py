@@ -175,11 +175,13 @@ class Engine(object):
         wait=False enqueues on the handle's stream (macm_step_host_async); call host_sync() before
         reading the returned pinned tensors."""
         p = self.pinned()
-        if actions_host.data_ptr() != p["actions"].data_ptr():
+        src = actions_host
+        if not (src.is_pinned() and src.is_contiguous()):   # pageable memory: stage it in the pinned mirror
             p["actions"].copy_(actions_host)
+            src = p["actions"]
         ptr = lambda n: C.c_void_p(p[n].data_ptr()) if (n in want and n in p) else None
         fn = _lib.lib().macm_step_host if wait else _lib.lib().macm_step_host_async
-        _lib.check(fn(self._h, C.c_void_p(p["actions"].data_ptr()), ptr("obs"), ptr("rewards"),
+        _lib.check(fn(self._h, C.c_void_p(src.data_ptr()), ptr("obs"), ptr("rewards"),
                       ptr("nn_idx"), ptr("collided"), ptr("done")), self._h)
         return p
 

@@ -66,3 +66,38 @@ def test_pade_damping_and_odd_iterations():
 
 def test_episode_done_step():
     run_parity(2, 4, 40, seed=16, time_limit=0.5, check_every=1)
+
+
+@pytest.mark.parametrize("N,cols", [(64, 8), (40, 8), (33, 11)])
+def test_nn_exact_draws_on_a_lattice(N, cols):
+    # agents on a square lattice (spacing 2 m: no contacts): every agent has two to four nearest
+    # neighbours at exactly the same squared distance, so the lowest index has to win
+    # (mvmnt.py:194, strict '<' in ascending order) -- the block-minimum search's draw handling,
+    # its rotated half and its padding lanes (N < 64) are all on this path
+    import torch
+    import gym_macm
+    from oracle import oracle
+    from _parity import compare_obs
+    E = 4
+    rng = np.random.default_rng(21)
+    idx = np.arange(N)
+    base = np.stack([2.0 * (idx % cols), 2.0 * (idx // cols)], -1).astype(np.float64)
+    pos = np.stack([base[rng.permutation(N)] + off for off in ((0, 0), (-7, 3), (100, -50), (0.5, 0.25))])
+    ang = rng.uniform(-3, 3, (E, N))
+    tg = rng.uniform(-40, 40, (E, 1, 2))
+    env = gym_macm.BatchedFlock(E, n_agents=[N], device="cuda:0", seed=None)
+    env.load_state(pos, ang, targets=tg)
+    ref = oracle.OracleBatch(E, n_agents=N, n_targets=1)
+    ref.reset(pos, ang, targets=tg)
+    torch.cuda.synchronize()
+    o = ref.flock_observe()
+    assert np.array_equal(env.state["nn_idx"].cpu().numpy(), o["nn_idx"])
+    compare_obs(env.state["obs"].cpu().numpy(), o, "polar")
+    idle = np.ones((E, N, 3), np.int64)
+    for k in range(3):   # the step kernel's own observation pass; idle agents stay on the lattice
+        env.step(torch.as_tensor(idle, device="cuda:0"))
+        o = ref.flock_step(idle)
+        torch.cuda.synchronize()
+        assert np.array_equal(env.state["nn_idx"].cpu().numpy(), o["nn_idx"]), "step %d" % k
+        compare_obs(env.state["obs"].cpu().numpy(), o, "polar", k)
+    env.close()
