@@ -26,8 +26,8 @@
 
 #include "macm_sim.h"
 
-// Launch shapes: 128-thread blocks, 7 per SM (72 registers); or, when the whole batch is one wave of
-// one-env-per-warp groups, one 896-thread block per SM.  (Measured on B200, profiles/README.md: the
+// Launch shapes: 128-thread blocks, 7 per SM (72 registers); or, for one-env-per-warp groups (N > 16),
+// one 896-thread block per SM.  (Measured on B200, profiles/README.md: the
 // warp scheduler favours the warps of the oldest resident block, so with seven small blocks the last
 // block's warps only get the issue slots the others leave and an env with large islands in that
 // block sets the kernel time; warps of one block are served evenly.)
@@ -1618,9 +1618,14 @@ cudaError_t macm_launch_cfg(const SimConst& P, int sm_count, LaunchCfg* cfg)
     pick_shape(P.N, &cfg->G, &cfg->APL);
     const int gpw = 32 / cfg->G;
     cfg->threads = 128;
-    // one wave of one-env-per-warp groups: a block per SM, envs dealt heavy-first inside it
+    // one-env-per-warp groups: a block per SM (profiles/README.md, finding 4) unless the last wave of such
+    // blocks would leave most SMs idle
     const int wide_warps = MACM_WIDE_THREADS / 32;
-    if (gpw == 1 && sm_count > 0 && (P.E + wide_warps - 1) / wide_warps <= sm_count && P.E > 4) cfg->threads = MACM_WIDE_THREADS;
+    if (gpw == 1 && sm_count > 0 && P.E >= wide_warps) {
+        const int wb = (P.E + wide_warps - 1) / wide_warps;
+        const int waves = (wb + sm_count - 1) / sm_count;
+        if (wb * 5 >= waves * sm_count * 4) cfg->threads = MACM_WIDE_THREADS;   // >= 80 % of the slots used
+    }
     if (const char* e = getenv("MACM_BLOCK_THREADS")) {   // experiments (profiles/README.md): 128 or 896
         const int t = atoi(e);
         if (t == 128 || (t == MACM_WIDE_THREADS && gpw == 1)) cfg->threads = t;
