@@ -189,6 +189,7 @@ def main():
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     E, N, ROT = args.envs, N_AGENTS, args.rot
@@ -202,10 +203,13 @@ def main():
     POOL = 61   # prime: batch r at its j-th step uses action set (j + 7 r) mod POOL, all distinct in sequence
     acts = torch.zeros((POOL, E, N, 4), dtype=torch.uint8, device=dev)
     acts[..., :3] = torch.randint(0, 3, (POOL, E, N, 3), generator=g, device=dev, dtype=torch.uint8)
-    gathered = None
+    gathered, gstream = None, None
     if args.gather and world > 1:
+        # learner-side exchange of BASELINE config 5: every rank receives every shard's obs + rewards.
+        # It runs on a side stream: the next batch steps while this batch's outputs cross NVLink.
         gathered = [torch.empty((world,) + tuple(sims[0].state[k].shape), dtype=sims[0].state[k].dtype, device=dev)
                     for k in ("obs", "rewards")]
+        gstream = torch.cuda.Stream(device=dev)
 
     def one_step(k):
         s = sims[k % ROT]
@@ -215,8 +219,10 @@ def main():
             a = acts[(k // ROT + 7 * (k % ROT)) % POOL]
         s.engine.step(a)
         if gathered is not None:
-            dist.all_gather_into_tensor(gathered[0], s.state["obs"])
-            dist.all_gather_into_tensor(gathered[1], s.state["rewards"])
+            gstream.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(gstream):
+                dist.all_gather_into_tensor(gathered[0], s.state["obs"])
+                dist.all_gather_into_tensor(gathered[1], s.state["rewards"])
 
     # settle: every batch runs SETTLE steps (1.07 s of simulated time of a 60 s / 3601-step episode)
     # so that the overlaps of the random spawn are resolved; then W warm-up steps of the rotation
@@ -235,6 +241,8 @@ def main():
     ev0.record()
     for k in range(args.steps):
         one_step(k)
+    if gstream is not None:
+        torch.cuda.current_stream(dev).wait_stream(gstream)   # the last gathers are part of the timed region
     ev1.record()
     torch.cuda.synchronize()
     t1 = time.time()
