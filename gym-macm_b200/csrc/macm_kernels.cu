@@ -189,6 +189,11 @@ __device__ __forceinline__ void b2normalize(float& x, float& y)
     y *= inv;
 }
 
+// sqrt for OUTPUTS only (observation distances, the linear reward): the reference computes them in
+// float64, the tests hold these floats to 1e-5 relative, and sqrt.approx is good to 1 ulp of fp32.
+// Engine state never goes through it (b2normalize, the translation clamp and the ray cast keep IEEE sqrtf).
+__device__ __forceinline__ float out_sqrtf(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 // t - sign(t)*2*pi if |t| > pi else t (mvmnt.py:199), in fp32 for the observation outputs
 __device__ __forceinline__ float wrap_pi_f(float t)
 {
@@ -573,11 +578,11 @@ __device__ void flock_observe(const Grp<G>& g, const EnvS<G * APL>& S, const Sim
         float nn_d = __int_as_float(0x7f800000), nn_t = 0.0f;
         if (bi[s] >= 0) {
             const float2 q = pos[bi[s]];
-            nn_d = sqrtf(best[s]);
+            nn_d = out_sqrtf(best[s]);
             nn_t = wrap_pi_f(fast_atan2f(q.y - o[s].y, q.x - o[s].x) - ang[s]);
         }
         const float tdx = tg[s].x - o[s].x, tdy = tg[s].y - o[s].y;
-        const float tg_r = sqrtf(tdx * tdx + tdy * tdy);
+        const float tg_r = out_sqrtf(tdx * tdx + tdy * tdy);
         const float tg_t = wrap_pi_f(fast_atan2f(tdy, tdx) - ang[s]);
         P.nn_idx[gi] = bi[s];
         if (P.coord == MACM_COORD_POLAR) reinterpret_cast<float4*>(P.obs)[gi] = make_float4(nn_d, nn_t, tg_r, tg_t);
@@ -617,7 +622,7 @@ __device__ void tdm_observe(const Grp<G>& g, const EnvS<G * APL>& S, const SimCo
             float4 v = make_float4(0.0f, 0.0f, 0.0f, -1.0f);
             if (ai && j != i && bit_of(alive, j)) {
                 const float dx = o[s].x - p.x, dy = o[s].y - p.y;
-                v.x = sqrtf(dx * dx + dy * dy);
+                v.x = out_sqrtf(dx * dx + dy * dy);
                 v.y = wrap_pi_f(fast_atan2f(dy, dx) - a);
                 v.z = wrap_pi_f(oa[s] - a);
                 v.w = (team[s] == ti) ? 1.0f : 0.0f;
@@ -837,20 +842,28 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
     // point, so a line the predecessor is still writing cannot go stale there), which takes the HBM
     // latency of the state off the critical path whenever there is a predecessor to overlap with.
     {
-        const int env_ = slot;
+        // one line per lane: 8 lanes on posvel, 8 on the fat AABBs (or the TDM state after the first 4), 4 on
+        // angle/sleep, 2 on the actions, 1 + 2 on the head of the contact list, then the per-env scalars
+        const int env_ = slot, l = g.gl;
         const size_t a0 = (size_t)env_ * P.N;
-        prefetch_l2<G>(g.gl, P.posvel + a0, P.N * 16);
-        prefetch_l2<G>(g.gl, P.fat + a0, P.N * 16);
-        prefetch_l2<G>(g.gl, P.angsleep + a0, P.N * 8);
-        prefetch_l2<G>(g.gl, (const char*)actions + a0 * (P.action_mode == MACM_ACTION_DISCRETE || TDM ? 4 : 8),
-                       P.N * (P.action_mode == MACM_ACTION_DISCRETE || TDM ? 4 : 8));
-        if (TDM) prefetch_l2<G>(g.gl, P.tdm + a0, P.N * 16);
-        prefetch_l2<G>(g.gl, P.c_ab + (size_t)env_ * P.C, 128);
-        prefetch_l2<G>(g.gl, P.c_imp + (size_t)env_ * P.C, 256);
-        if (g.gl == 0) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(P.env_state + env_));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(P.c_cnt + env_));
-            if (!TDM) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.targets + (size_t)env_ * P.T));
+        const int abytes = (TDM || P.action_mode == MACM_ACTION_DISCRETE) ? 4 : 8;
+        const char* p = nullptr;
+        int off = 0, lim = 0;
+        if (l < 8) { p = (const char*)(P.posvel + a0); off = l * 128; lim = P.N * 16; }
+        else if (l < 16) { p = (const char*)(P.fat + a0); off = (l - 8) * 128; lim = P.N * 16; }
+        else if (l < 20) { p = (const char*)(P.angsleep + a0); off = (l - 16) * 128; lim = P.N * 8; }
+        else if (l < 24) { p = (const char*)actions + a0 * abytes; off = (l - 20) * 128; lim = P.N * abytes; }
+        else if (l < 25) { p = (const char*)(P.c_ab + (size_t)env_ * P.C); lim = 1; }
+        else if (l < 27) { p = (const char*)(P.c_imp + (size_t)env_ * P.C); off = (l - 25) * 128; lim = 256; }
+        else if (l < 28) { p = (const char*)(P.env_state + env_); lim = 1; }
+        else if (l < 29) { p = (const char*)(P.c_cnt + env_); lim = 1; }
+        else if (l < 30) { if (!TDM) { p = (const char*)(P.targets + (size_t)env_ * P.T); lim = 1; } }
+        if (G == 32 && off < lim) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
+        if (G == 32 && TDM) prefetch_l2<G>(g.gl, P.tdm + a0, P.N * 16);
+        if (G < 32) {   // several envs per warp: a few lines each
+            prefetch_l2<G>(g.gl, P.posvel + a0, P.N * 16);
+            prefetch_l2<G>(g.gl, P.fat + a0, P.N * 16);
+            prefetch_l2<G>(g.gl, P.angsleep + a0, P.N * 8);
         }
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -1454,7 +1467,7 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
             const float2 tg = S.tgt()[i];
             const float dx = tg.x - c[s].x, dy = tg.y - c[s].y;
             const float d2 = dx * dx + dy * dy;
-            if (P.reward_mode == MACM_REWARD_LINEAR) rew = (-sqrtf(d2) / 35.0f) + 1.0f;
+            if (P.reward_mode == MACM_REWARD_LINEAR) rew = 1.0f - out_sqrtf(d2) * (1.0f / 35.0f);   // 1 - d/35 (mvmnt.py:179), float64 there
             else rew = (d2 < P.binary_thr) ? 1.0f : 0.0f;
         }
         P.rewards[gi] = rew;
