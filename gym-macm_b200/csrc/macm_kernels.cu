@@ -415,21 +415,24 @@ __device__ int find_new_contacts(const Grp<G>& g, const EnvS<G * APL>& S, const 
 // The reference keeps the lowest index among equal minima (strict '<' in ascending order,
 // mvmnt.py:194).  The broadcast half is visited in ascending order, so there the first block wins
 // and the lowest index inside it is taken; the rotated half is not, so an exact tie between a
-// block's minimum and the running minimum raises a flag and that agent is re-scanned in order
-// (nn_rescan: about one agent-step in 10^5).
+// block's minimum and the running minimum raises a flag and that agent is searched again, exactly, by
+// the whole group (nn_rescan; about 3 % of the warps have such an agent in a step).
 // ------------------------------------------------------------------------------------------
-template <int NC>
-__device__ __noinline__ float2 nn_rescan(const float2* pos, float2 o, int self)
+// Exact nearest other agent of ONE agent (position o, index self), by the whole group: lane j looks at
+// candidates j and j + 32, the minimum goes through a warp reduction on the bit patterns (squared
+// distances are non-negative, so unsigned order is float order) and the lowest index holding it wins.
+template <int G>
+__device__ __noinline__ float2 nn_rescan(const Grp<G>& g, const float2* pos, float2 o, int self)
 {
-    float best = __int_as_float(0x7f800000);
-    int bi = -1;
-    for (int j = 0; j < NC; ++j) {
-        const float2 q = pos[j];
-        const float dx = q.x - o.x, dy = q.y - o.y;
-        const float d2 = dx * dx + dy * dy;
-        if (j != self && d2 < best) { best = d2; bi = j; }
-    }
-    return make_float2(best, __int_as_float(bi));
+    const float2 qa = pos[g.gl], qb = pos[g.gl + 32];
+    const float ax = qa.x - o.x, ay = qa.y - o.y, bx = qb.x - o.x, by = qb.y - o.y;
+    unsigned da = __float_as_uint(ax * ax + ay * ay), db = __float_as_uint(bx * bx + by * by);
+    if (g.gl == self) da = 0xffffffffu;
+    if (g.gl + 32 == self) db = 0xffffffffu;
+    const unsigned m = __reduce_min_sync(g.mask, min(da, db));
+    const unsigned la = g.ballot(da == m), lb = g.ballot(db == m);
+    const int idx = la ? (__ffs((int)la) - 1) : (32 + __ffs((int)lb) - 1);
+    return make_float2(__uint_as_float(m), __int_as_float(idx));
 }
 
 #define NN_D2(q, OX, OY, dl, dh)                                                             \
@@ -511,9 +514,23 @@ __device__ __forceinline__ void nn_search_64(const Grp<G>& g, const EnvS<2 * G>&
         if (in0 && d0 == best0) bi0 = min(bi0, c0);
         if (in1 && d1 == best1) bi1 = min(bi1, c1);
     }
-    // an exact draw in the rotated half (or nothing found: every other agent infinitely far): in order, from scratch
-    if ((own0 && tie0) || bi0 == 64) { const float2 r = nn_rescan<64>(pos, o0, g.gl); best0 = r.x; bi0 = __float_as_int(r.y); }
-    if ((own1 && tie1) || bi1 == 64) { const float2 r = nn_rescan<64>(pos, o1, g.gl + 32); best1 = r.x; bi1 = __float_as_int(r.y); }
+    // an exact draw in the rotated half (about one agent in 4,000: two of its 63 squared distances collide):
+    // that agent is searched again, exactly, by the whole group
+    {
+        unsigned n0 = g.ballot((own0 && tie0) || bi0 == 64), n1 = g.ballot((own1 && tie1) || bi1 == 64);
+        for (; n0; n0 &= n0 - 1) {
+            const int src = __ffs((int)n0) - 1;
+            const float2 oo = make_float2(__shfl_sync(g.mask, o0.x, src), __shfl_sync(g.mask, o0.y, src));
+            const float2 r = nn_rescan<G>(g, pos, oo, src);
+            if (g.gl == src) { best0 = r.x; bi0 = __float_as_int(r.y); }
+        }
+        for (; n1; n1 &= n1 - 1) {
+            const int src = __ffs((int)n1) - 1;
+            const float2 oo = make_float2(__shfl_sync(g.mask, o1.x, src), __shfl_sync(g.mask, o1.y, src));
+            const float2 r = nn_rescan<G>(g, pos, oo, src + 32);
+            if (g.gl == src) { best1 = r.x; bi1 = __float_as_int(r.y); }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
