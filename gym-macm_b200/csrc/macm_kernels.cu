@@ -32,6 +32,9 @@
 // block's warps only get the issue slots the others leave and an env with large islands in that
 // block sets the kernel time; warps of one block are served evenly.)
 #define MACM_WIDE_THREADS 896
+#ifndef MACM_SMALL_BLOCKS
+#define MACM_SMALL_BLOCKS 7   // several envs per warp (N <= 16): 128-thread blocks; 8 or 9 blocks (64 / 56 registers) measured no faster
+#endif
 
 // Phase stamps for profiles/phase_trace.py (a separate build with -DMACM_PHASE_TRACE; the trace
 // buffer then holds 16 words per env: SM clock at the end of each phase, relative to the start).
@@ -831,7 +834,7 @@ __device__ __noinline__ int fresh_world_contacts(const Grp<G>& g, const EnvS<G *
 // the step kernel
 // ------------------------------------------------------------------------------------------
 template <int G, int APL, int KIND>
-__global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const __grid_constant__ SimConst P,
+__global__ void __launch_bounds__((G == 32 ? MACM_WIDE_THREADS : 128), (G == 32 ? 1 : MACM_SMALL_BLOCKS)) macm_step_kernel(const __grid_constant__ SimConst P,
                                                         const void* __restrict__ actions)
 {
     constexpr int NC = G * APL;
