@@ -32,6 +32,7 @@
 // block's warps only get the issue slots the others leave and an env with large islands in that
 // block sets the kernel time; warps of one block are served evenly.)
 #define MACM_WIDE_THREADS 896
+#define MACM_TABLE_BYTES (418 * 16)   // sin/cos(k/128) as double2, staged per block in the wide launch
 #ifndef MACM_SMALL_BLOCKS
 #define MACM_SMALL_BLOCKS 7   // several envs per warp (N <= 16): 128-thread blocks; 8 or 9 blocks (64 / 56 registers) measured no faster
 #endif
@@ -237,7 +238,7 @@ __device__ __forceinline__ void sincos_f32arg(const double2* __restrict__ tab, f
 {
     const float fk = rintf(fabsf(Af) * 128.0f);
     if (!(fk <= 416.0f)) { sincos_slow(Af, &s, &c); return; }
-    const double2 sc = __ldg(&tab[(int)fk]);
+    const double2 sc = tab[(int)fk];
     const double x = fabs((double)Af) - (double)fk * 0.0078125;
     const double x2 = x * x;
     // sin x = x + x^3 (-1/6 + x^2 (1/120 - x^2/5040)) ; cos x - 1 = x^2 (-1/2 + x^2 (1/24 + x^2 (-1/720 + x^2/40320)))
@@ -844,6 +845,16 @@ __global__ void __launch_bounds__((G == 32 ? MACM_WIDE_THREADS : 128), (G == 32 
     const Grp<G> g;
     const int slot_in_block = (threadIdx.x >> 5) * GPW + (threadIdx.x & 31) / G;
     const int slot = blockIdx.x * (blockDim.x / 32) * GPW + slot_in_block;
+    // One block per SM: the sin/cos table of the action decode (library-owned, written once at
+    // macm_create) is copied to shared memory before anything else -- under programmatic dependent launch
+    // that happens while the previous kernel drains, and phase 1 no longer waits for L2.
+    const double2* sincos_tab = P.sincos_tab;
+    if (blockDim.x > 128) {
+        double2* tab_s = reinterpret_cast<double2*>(smem_raw + (size_t)(blockDim.x / 32) * GPW * Lay<NC>::bytes(P.TC));
+        for (int k = threadIdx.x; k < MACM_TABLE_BYTES / 16; k += blockDim.x) tab_s[k] = __ldg(&P.sincos_tab[k]);
+        __syncthreads();
+        sincos_tab = tab_s;
+    }
     if (slot >= P.E) return;  // whole group leaves together
     unsigned long long tr_t0 = 0, tr_c0 = 0;
     const int N = P.N;
@@ -968,7 +979,7 @@ __global__ void __launch_bounds__((G == 32 ? MACM_WIDE_THREADS : 128), (G == 32 
             // t = fl(A + pi/2) = (A + pi/2) + d exactly, with d from the rounding error of the sum and
             // the tail of pi/2, so cos t = -sin(A + d) = -(sin A + d cos A), sin t = cos A - d sin A.
             double s1, c1;
-            sincos_f32arg(P.sincos_tab, af, s1, c1);
+            sincos_f32arg(sincos_tab, af, s1, c1);
             const double A = (double)af, H = NP_PI / 2;
             const double t = A + H, bb = t - A;
             const double err = (A - (t - bb)) + (H - bb);          // A + H == t + err exactly (TwoSum)
@@ -1675,12 +1686,12 @@ cudaError_t macm_launch_cfg(const SimConst& P, int sm_count, LaunchCfg* cfg)
         default: per_env = Lay<64>::bytes(P.TC); break;
     }
     cfg->per_env_bytes = per_env;
-    if (per_env * cfg->envs_per_block > 227 * 1024) {   // fall back to narrow blocks
+    if (per_env * cfg->envs_per_block + MACM_TABLE_BYTES > 227 * 1024) {   // fall back to narrow blocks
         cfg->threads = 128;
         cfg->envs_per_block = 4 * gpw;
         cfg->blocks = (P.E + cfg->envs_per_block - 1) / cfg->envs_per_block;
     }
-    cfg->smem_bytes = per_env * cfg->envs_per_block;
+    cfg->smem_bytes = per_env * cfg->envs_per_block + (cfg->threads > 128 ? MACM_TABLE_BYTES : 0);   // + sin/cos table
     cfg->obs_blocks = (P.E + 4 * gpw - 1) / (4 * gpw);
     cfg->obs_smem_bytes = per_env * 4 * gpw;
     return cfg->smem_bytes <= 227 * 1024 ? cudaSuccess : cudaErrorInvalidConfiguration;
