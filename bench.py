@@ -189,9 +189,20 @@ def main():
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries the one JSON line only: NCCL's banner ("NCCL version ...", printed to stdout when the
+        # communicator is created) goes to stderr
+        sys.stdout.flush()
+        keep = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(keep, 1)
+            os.close(keep)
     E, N, ROT = args.envs, N_AGENTS, args.rot
 
     extra = {"max_touching": args.max_touching} if args.max_touching else {}
