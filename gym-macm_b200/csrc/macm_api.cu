@@ -321,7 +321,43 @@ extern "C" int macm_step(macm_sim* sim, const void* actions, void* stream)
     if (!sim || !actions) return MACM_E_INVALID;
     if (!sim->bound) return MACM_E_UNBOUND;
     if (!aligned(actions, sim->params.action_mode == MACM_ACTION_DISCRETE ? 4 : 8)) return MACM_E_ALIGN;
-    CU(macm_launch_step(sim->K, sim->cfg, actions, (cudaStream_t)stream));
+    Rollout R = {};
+    R.K = 1;
+    R.policy = -1;
+    CU(macm_launch_step(sim->K, sim->cfg, actions, R, (cudaStream_t)stream));
+    sim->launches += 1;
+    return MACM_OK;
+}
+
+extern "C" int macm_rollout(macm_sim* sim, const void* actions, int32_t n_steps, int32_t policy, uint64_t seed,
+                            const macm_rollout_out* out, void* stream)
+{
+    if (!sim || n_steps < 1) return MACM_E_INVALID;
+    if (!sim->bound) return MACM_E_UNBOUND;
+    const bool discrete = sim->params.action_mode == MACM_ACTION_DISCRETE;
+    Rollout R = {};
+    R.K = n_steps;
+    R.policy = -1;
+    R.seed = seed;
+    R.sync = sim->cfg.threads > 128 ? 1 : 0;   // wide blocks: the warps of a block run each step in step
+    if (const char* e = getenv("MACM_ROLLOUT_SYNC")) R.sync = atoi(e);   // experiments
+    if (actions) {
+        if (!aligned(actions, discrete ? 4 : 8)) return MACM_E_ALIGN;
+    } else {
+        // actions=None: every agent's actor decides from its own observation (mvmnt.py:86-92)
+        if (policy < MACM_BOT_IDLE || policy > MACM_BOT_RANDOM) return policy == MACM_BOT_COMBAT ? MACM_E_UNSUPPORTED : MACM_E_INVALID;
+        if (!discrete) return MACM_E_UNSUPPORTED;
+        if (policy == MACM_BOT_FLOCK && (sim->K.kind != MACM_ENV_FLOCK || sim->params.coord != MACM_COORD_POLAR))
+            return MACM_E_UNSUPPORTED;
+        R.policy = policy;
+    }
+    if (out) {
+        if ((out->obs && !aligned(out->obs, 16)) || (out->rewards && !aligned(out->rewards, 4)) ||
+            (out->nn_idx && !aligned(out->nn_idx, 4)))
+            return MACM_E_ALIGN;
+        R.obs = out->obs; R.nn_idx = out->nn_idx; R.rewards = out->rewards; R.collided = out->collided; R.done = out->done;
+    }
+    CU(macm_launch_step(sim->K, sim->cfg, actions, R, (cudaStream_t)stream));
     sim->launches += 1;
     return MACM_OK;
 }
@@ -366,7 +402,10 @@ extern "C" int macm_step_host_async(macm_sim* sim, const void* actions, float* o
     }
     cudaStream_t s = sim->hstream;
     CU(cudaMemcpyAsync(sim->d_actions, actions, abytes, cudaMemcpyHostToDevice, s));
-    CU(macm_launch_step(sim->K, sim->cfg, sim->d_actions, s));
+    Rollout R = {};
+    R.K = 1;
+    R.policy = -1;
+    CU(macm_launch_step(sim->K, sim->cfg, sim->d_actions, R, s));
     sim->launches += 1;
     if (obs) CU(cudaMemcpyAsync(obs, sim->K.obs, z.obs, cudaMemcpyDeviceToHost, s));
     if (rewards) CU(cudaMemcpyAsync(rewards, sim->K.rewards, z.rewards, cudaMemcpyDeviceToHost, s));

@@ -5,31 +5,6 @@
 
 namespace {
 
-// Philox4x32-10 (Salmon et al., SC'11): counter-based, so a draw is a pure function of
-// (seed, index, stream) and does not depend on launch geometry.
-struct Philox {
-    uint32_t c[4];
-    __device__ Philox(uint64_t seed, uint64_t index, uint32_t stream, uint32_t sub)
-    {
-        uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-        c[0] = (uint32_t)index; c[1] = (uint32_t)(index >> 32); c[2] = stream; c[3] = sub;
-#pragma unroll
-        for (int r = 0; r < 10; ++r) {
-            const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-            const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
-            c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
-            k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-        }
-    }
-    // 53-bit uniform in [0, 1), the construction CPython's random.random() uses
-    __device__ double u53(int pair) const
-    {
-        const uint32_t a = c[pair * 2] >> 5, b = c[pair * 2 + 1] >> 6;
-        return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
-    }
-};
-
 __global__ void macm_sample_kernel(const __grid_constant__ SimConst P, uint64_t seed, double spread, double sx,
                                    double sy, double tmin, double tmax, double width, double height)
 {

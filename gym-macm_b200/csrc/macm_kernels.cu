@@ -552,8 +552,12 @@ __device__ __noinline__ void store_cartesian(float* obs, size_t gi, float nn_d, 
     ob[2] = make_float2(ct, st);
 }
 
+// Destinations: (ob1, nn1) and (ob2, nn2), each pointer may be null (a rollout writes a step's observation to
+// the caller's per-step arrays and, on its last step, to the sim's bound buffers as well).  tgo, when not null,
+// receives every agent's target node (r, theta), indexed by agent -- what the flock actor of bots.py steers by.
 template <int G, int APL>
-__device__ void flock_observe(const Grp<G>& g, const EnvS<G * APL>& S, const SimConst& P, int env, const float* ang)
+__device__ void flock_observe(const Grp<G>& g, const EnvS<G * APL>& S, const SimConst& P, int env, const float* ang,
+                              float* ob1, int* nn1, float* ob2, int* nn2, float2* tgo = nullptr)
 {
     const float2* pos = S.pos();
     const int N = P.N;
@@ -605,9 +609,17 @@ __device__ void flock_observe(const Grp<G>& g, const EnvS<G * APL>& S, const Sim
         const float tdx = tg[s].x - o[s].x, tdy = tg[s].y - o[s].y;
         const float tg_r = out_sqrtf(tdx * tdx + tdy * tdy);
         const float tg_t = wrap_pi_f(fast_atan2f(tdy, tdx) - ang[s]);
-        P.nn_idx[gi] = bi[s];
-        if (P.coord == MACM_COORD_POLAR) reinterpret_cast<float4*>(P.obs)[gi] = make_float4(nn_d, nn_t, tg_r, tg_t);
-        else store_cartesian(P.obs, gi, nn_d, nn_t, tg_r, tg_t);
+        if (tgo) tgo[i] = make_float2(tg_r, tg_t);
+        if (nn1) nn1[gi] = bi[s];
+        if (nn2) nn2[gi] = bi[s];
+        if (P.coord == MACM_COORD_POLAR) {
+            const float4 o4 = make_float4(nn_d, nn_t, tg_r, tg_t);
+            if (ob1) reinterpret_cast<float4*>(ob1)[gi] = o4;
+            if (ob2) reinterpret_cast<float4*>(ob2)[gi] = o4;
+        } else {
+            if (ob1) store_cartesian(ob1, gi, nn_d, nn_t, tg_r, tg_t);
+            if (ob2) store_cartesian(ob2, gi, nn_d, nn_t, tg_r, tg_t);
+        }
     }
 }
 
@@ -615,7 +627,8 @@ __device__ void flock_observe(const Grp<G>& g, const EnvS<G * APL>& S, const Sim
 // [r, theta, phi] and the ally flag.  Row i of the [N,N,4] output is written by the whole group
 // (lane <-> j) so that the 16-byte stores of a row are contiguous.
 template <int G, int APL>
-__device__ void tdm_observe(const Grp<G>& g, const EnvS<G * APL>& S, const SimConst& P, int env, uint2 alive)
+__device__ void tdm_observe(const Grp<G>& g, const EnvS<G * APL>& S, const SimConst& P, int env, uint2 alive,
+                            float* ob1, float* ob2)
 {
     const float2* pos = S.pos();
     const float* angs = S.ang();
@@ -630,7 +643,8 @@ __device__ void tdm_observe(const Grp<G>& g, const EnvS<G * APL>& S, const SimCo
         oa[s] = angs[j];
         team[s] = j < N ? P.team[j] : 0;
     }
-    float4* out = reinterpret_cast<float4*>(P.obs) + (size_t)env * N * N;
+    float4* out = ob1 ? reinterpret_cast<float4*>(ob1) + (size_t)env * N * N : nullptr;
+    float4* out2 = ob2 ? reinterpret_cast<float4*>(ob2) + (size_t)env * N * N : nullptr;
     for (int i = 0; i < N; ++i) {
         const float2 p = pos[i];
         const float a = angs[i];
@@ -648,7 +662,8 @@ __device__ void tdm_observe(const Grp<G>& g, const EnvS<G * APL>& S, const SimCo
                 v.z = wrap_pi_f(oa[s] - a);
                 v.w = (team[s] == ti) ? 1.0f : 0.0f;
             }
-            out[(size_t)i * N + j] = v;
+            if (out) out[(size_t)i * N + j] = v;
+            if (out2) out2[(size_t)i * N + j] = v;
         }
     }
 }
@@ -831,13 +846,59 @@ __device__ __noinline__ int fresh_world_contacts(const Grp<G>& g, const EnvS<G *
     return cnt;
 }
 
+// The scripted actors of test_scripts/bots.py inside a rollout (the actions=None mode of mvmnt.py:86-92):
+// the same rules and the same counter-based draws as macm_bot_kernel (macm_aux.cu).  tn = the agent's target
+// node (r, theta) of the last observation.
+__device__ __forceinline__ uint32_t bot_action(const SimConst& P, const Rollout& R, float2 tn, int env, int i, int step)
+{
+    uint32_t a0 = 1, a1 = 1, a2 = 1, a3 = 0;
+    switch (R.policy) {
+        case MACM_BOT_FORWARD: a0 = 2; break;
+        case MACM_BOT_ROTATE: a2 = 2; break;
+        case MACM_BOT_DIAG: a0 = 2; a1 = 2; break;
+        case MACM_BOT_RANDOM: {
+            const uint64_t gi = (uint64_t)env * P.N + i;
+            const Philox r(R.seed, gi + (uint64_t)P.env_base * P.N, 2u, (uint32_t)step);
+            a0 = (uint32_t)(((uint64_t)r.c[0] * 3u) >> 32);
+            a1 = (uint32_t)(((uint64_t)r.c[1] * 3u) >> 32);
+            a2 = (uint32_t)(((uint64_t)r.c[2] * 3u) >> 32);
+            a3 = P.kind == MACM_ENV_TDM ? (r.c[3] >> 31) : 0u;
+            break;
+        }
+        case MACM_BOT_FLOCK: {
+            const float th_sign = (tn.y > 0.0f) ? 1.0f : (tn.y < 0.0f ? -1.0f : 0.0f);
+            const float ahead = fabsf(tn.y) < (float)(NP_PI / 4) ? 1.0f : 0.0f;
+            if (!(tn.x < 1.0f)) { a2 = (uint32_t)(th_sign + 1.0f); a0 = (uint32_t)(ahead + 1.0f); }
+            break;
+        }
+        default: break;
+    }
+    return a0 | (a1 << 8) | (a2 << 16) | (a3 << 24);
+}
+
 // ------------------------------------------------------------------------------------------
 // the step kernel
 // ------------------------------------------------------------------------------------------
-template <int G, int APL, int KIND>
+// ROLL = false: one step per launch (macm_step); every rollout argument folds away at compile time.
+// ROLL = true: R.K steps per launch (macm_rollout), the env's bodies staying in registers / shared memory.
+template <int G, int APL, int KIND, bool ROLL>
 __global__ void __launch_bounds__((G == 32 ? MACM_WIDE_THREADS : 128), (G == 32 ? 1 : MACM_SMALL_BLOCKS)) macm_step_kernel(const __grid_constant__ SimConst P,
-                                                        const void* __restrict__ actions)
+                                                        const void* __restrict__ actions,
+                                                        const __grid_constant__ Rollout R_)
 {
+    // the single-step kernel sees compile-time constants instead of the rollout arguments
+    struct RollView {
+        const Rollout& r;
+        __device__ int K() const { return ROLL ? r.K : 1; }
+        __device__ int policy() const { return ROLL ? r.policy : -1; }
+        __device__ int sync() const { return ROLL ? r.sync : 0; }
+        __device__ float* obs() const { return ROLL ? r.obs : nullptr; }
+        __device__ int* nn_idx() const { return ROLL ? r.nn_idx : nullptr; }
+        __device__ float* rewards() const { return ROLL ? r.rewards : nullptr; }
+        __device__ uint8_t* collided() const { return ROLL ? r.collided : nullptr; }
+        __device__ uint8_t* done() const { return ROLL ? r.done : nullptr; }
+    };
+    const RollView R{R_};
     constexpr int NC = G * APL;
     constexpr int GPW = 32 / G;
     constexpr bool TDM = KIND == MACM_ENV_TDM;
@@ -883,7 +944,7 @@ __global__ void __launch_bounds__((G == 32 ? MACM_WIDE_THREADS : 128), (G == 32 
         if (l < 8) { p = (const char*)(P.posvel + a0); off = l * 128; lim = P.N * 16; }
         else if (l < 16) { p = (const char*)(P.fat + a0); off = (l - 8) * 128; lim = P.N * 16; }
         else if (l < 20) { p = (const char*)(P.angsleep + a0); off = (l - 16) * 128; lim = P.N * 8; }
-        else if (l < 24) { p = (const char*)actions + a0 * abytes; off = (l - 20) * 128; lim = P.N * abytes; }
+        else if (l < 24) { if (actions) { p = (const char*)actions + a0 * abytes; off = (l - 20) * 128; lim = P.N * abytes; } }
         else if (l < 25) { p = (const char*)(P.c_ab + (size_t)env_ * P.C); lim = 1; }
         else if (l < 27) { p = (const char*)(P.c_imp + (size_t)env_ * P.C); off = (l - 25) * 128; lim = 256; }
         else if (l < 28) { p = (const char*)(P.env_state + env_); lim = 1; }
@@ -910,8 +971,8 @@ __global__ void __launch_bounds__((G == 32 ? MACM_WIDE_THREADS : 128), (G == 32 
     float4 fatr[APL];
     bool valid[APL];
     uint32_t act_raw[APL];
-    uint2 alive = make_uint2(0u, 0u);   // bodies that are active (have a proxy) during this step
-    const int4 es = P.env_state[env];
+    const int4 es0 = P.env_state[env];
+    int step_cnt = es0.x, eflags = es0.y, winner = es0.w;   // b2World step count, MACM_ENV_* bits, TDM winner
     int cnt = P.c_cnt[env];
     // first chunk of the contact list, fetched together with the state (one HBM round trip less)
     uint32_t pre_ab = 0u;
@@ -944,14 +1005,55 @@ __global__ void __launch_bounds__((G == 32 ? MACM_WIDE_THREADS : 128), (G == 32 
             c[s] = make_float2(3.0e30f, 3.0e30f); v[s] = make_float2(0.0f, 0.0f);
             fatr[s] = make_float4(3.0e30f, 3.0e30f, 3.0e30f, 3.0e30f);
         }
+        if (!TDM) S.tgt()[i] = P.targets[(size_t)env * P.T + P.target_idx[valid[s] ? i : 0]];
+        // the flock actor steers by the target node of the last observation (bots.py:37-61)
+        if (!TDM && R.policy() == MACM_BOT_FLOCK && valid[s]) {
+            const float4 o4 = reinterpret_cast<const float4*>(P.obs)[gi];   // polar only (macm_rollout checks)
+            reinterpret_cast<float2*>(S.nw())[i] = make_float2(o4.z, o4.w);
+        }
+    }
+    const bool discrete = TDM || P.action_mode == MACM_ACTION_DISCRETE;
+    const size_t EN = (size_t)P.E * N;
+    int tc = 0, nlev = 0;
+    bool multi = false;
+
+    // ---- K steps of this env; its state stays in registers / shared memory between them -------------
+#pragma unroll 1
+    for (int ks = 0; ks < R.K(); ++ks) {
+    const bool last = ks == R.K() - 1;
+    uint2 alive = make_uint2(0u, 0u);   // bodies that are active (have a proxy) during this step
+    // The block's warps start every R.sync()-th step together.  Measured (profiles/README.md, finding 8): the hot
+    // path is ~48 KB of straight-line code; warps that drift apart each stream it from the GPC-level instruction
+    // cache on their own, which saturates (gcc requests 83 % of peak, "no instruction" the top stall) -- in step
+    // they share every fetched line.
+    if (R.sync() > 0 && ks > 0 && (ks % R.sync()) == 0) __syncthreads();
+    if (R.sync() < 0 && ks > 0 && G == 32 && (ks % (-R.sync())) == 0) {
+        // the warps of one sub-partition (warp id mod 4) start the step together: they share that sub-partition's L0
+        const int warps_live = min((int)blockDim.x / 32, P.E - (int)blockIdx.x * ((int)blockDim.x / 32));
+        const int q = (threadIdx.x >> 5) & 3;
+        const int members = (warps_live - q + 3) / 4;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(members * 32) : "memory");
+    }
+    g.sync();   // the previous step's observation pass has finished reading the staging arrays
+#pragma unroll
+    for (int s = 0; s < APL; ++s) {
+        const int i = g.gl + s * G;
+        const size_t gi = (size_t)env * N + (valid[s] ? i : 0);
         pos[i] = c[s];
         fat[i] = fatr[s];
         adj[i] = make_uint2(0u, 0u);
         S.tmask()[i] = 0u;
-        if (!TDM) S.tgt()[i] = P.targets[(size_t)env * P.T + P.target_idx[valid[s] ? i : 0]];
-        // discrete action word, fetched with the state
+        // discrete action word, fetched with the state (first step) / one step ahead into L2 (later steps)
         act_raw[s] = 0u;
-        if ((TDM || P.action_mode == MACM_ACTION_DISCRETE) && valid[s]) act_raw[s] = reinterpret_cast<const uint32_t*>(actions)[gi];
+        if (discrete && valid[s]) {
+            if (!ROLL || actions) {
+                const uint32_t* aw = reinterpret_cast<const uint32_t*>(actions) + (size_t)ks * EN + gi;
+                act_raw[s] = *aw;
+                if (!last) asm volatile("prefetch.global.L2 [%0];" ::"l"(aw + EN));
+            } else {
+                act_raw[s] = bot_action(P, R_, reinterpret_cast<const float2*>(S.nw())[i], env, i, step_cnt);
+            }
+        }
     }
 
     PHASE_STAMP(0);
@@ -1008,7 +1110,7 @@ __global__ void __launch_bounds__((G == 32 ? MACM_WIDE_THREADS : 128), (G == 32 
                 if ((P.flags & MACM_FLAG_REPAIR_MOV_COOLDOWN) && !started && cd_mov[s] > 0) cd_mov[s] -= 1;
             }
         } else {
-            const float2 ac = reinterpret_cast<const float2*>(actions)[gi];
+            const float2 ac = reinterpret_cast<const float2*>(actions)[(size_t)ks * EN + gi];
             double x = (double)ac.x, y = (double)ac.y;
             if ((x * x + y * y) > 1) {  // bug-compatible with mvmnt.py:124-126
                 x = sqrt(x * x / (x * x + y * y));
@@ -1095,13 +1197,13 @@ __global__ void __launch_bounds__((G == 32 ? MACM_WIDE_THREADS : 128), (G == 32 
 
     PHASE_STAMP(2);
     // ---- phase 2a: new fixtures -> FindNewContacts before Collide (b2World::Step prologue) ----
-    if (es.y & MACM_ENV_FRESH) cnt = fresh_world_contacts<G, APL>(g, S, P, alive, cnt, c_ab, c_imp, overflow_c);
+    if (eflags & MACM_ENV_FRESH) cnt = fresh_world_contacts<G, APL>(g, S, P, alive, cnt, c_ab, c_imp, overflow_c);
 
     // ---- phase 2: b2ContactManager::Collide --------------------------------------------------
     // destroy contacts whose fat AABBs stopped overlapping (or whose body was deactivated),
     // narrowphase the rest, compact in place (birth order is preserved), stage the touching ones
-    int tc = 0;
-    bool multi = false;   // some body has two touching contacts: islands are more than pairs
+    tc = 0;
+    multi = false;   // some body has two touching contacts: islands are more than pairs
     {
         float2* t_imp = S.t_imp();
         uint32_t* t_ew = S.t_ew();
@@ -1114,7 +1216,7 @@ __global__ void __launch_bounds__((G == 32 ? MACM_WIDE_THREADS : 128), (G == 32 
             uint32_t ab = 0;
             float2 imp = make_float2(0.0f, 0.0f);
             if (in) {
-                if (base == 0 && !(es.y & MACM_ENV_FRESH)) { ab = pre_ab; imp = pre_imp; }
+                if (base == 0 && ks == 0 && !(eflags & MACM_ENV_FRESH)) { ab = pre_ab; imp = pre_imp; }
                 else { ab = c_ab[k]; imp = c_imp[k]; }
             }
             g.sync();  // every lane holds its record before any lane compacts over it
@@ -1192,12 +1294,12 @@ __global__ void __launch_bounds__((G == 32 ? MACM_WIDE_THREADS : 128), (G == 32 
     //     level-scheduled across lanes (islands_big / solve_*_big, out of line).
     const bool big = tc > G;
     const bool has = !big && g.gl < tc;
-    int nlev = 0;
+    nlev = 0;
     int ka = 0, kb = 0;
     float knx = 1.0f, kny = 0.0f, knI = 0.0f, ktI = 0.0f;
     int ohead = EW_NONE, oseed = 0;     // multi: first contact of this lane's island, its seed body
     // inv_dt0 == 0 on a world's first step -> dtRatio 0
-    const float ratio = (es.x == 0) ? 0.0f : P.dt_ratio;
+    const float ratio = (step_cnt == 0) ? 0.0f : P.dt_ratio;
 
     // ---- phase 5: contact solver, velocity part -------------------------------------------------
     if (big) {
@@ -1469,9 +1571,8 @@ __global__ void __launch_bounds__((G == 32 ? MACM_WIDE_THREADS : 128), (G == 32 
 
     PHASE_STAMP(10);
     // ---- phase 11: rewards (mvmnt.py:160-179), time/done (mvmnt.py:134-136) ---------------------------
-    const int step = es.x + 1;
+    const int step = step_cnt + 1;
     bool done = step >= P.done_step;
-    int winner = es.w;
     if (TDM) {
         // alive_teams (combat.py:172-182)
         int teams_alive = 0, last = -1;
@@ -1501,39 +1602,55 @@ __global__ void __launch_bounds__((G == 32 ? MACM_WIDE_THREADS : 128), (G == 32 
             if (P.reward_mode == MACM_REWARD_LINEAR) rew = 1.0f - out_sqrtf(d2) * (1.0f / 35.0f);   // 1 - d/35 (mvmnt.py:179), float64 there
             else rew = (d2 < P.binary_thr) ? 1.0f : 0.0f;
         }
+        if (R.rewards()) R.rewards()[(size_t)ks * EN + gi] = rew;
+        if (R.collided()) R.collided()[(size_t)ks * EN + gi] = (uint8_t)col;
+        if (TDM) S.ang()[i] = ang[s];
+        if (!last) continue;
         P.rewards[gi] = rew;
         P.collided[gi] = (uint8_t)col;
-        // ---- phase 12: write state back ----
+        // ---- phase 12: write state back (last step of the launch) ----
         P.posvel[gi] = make_float4(c[s].x, c[s].y, v[s].x, v[s].y);
         P.angsleep[gi] = make_float2(ang[s], slp[s]);
         P.fat[gi] = fatr[s];
-        if (TDM) {
-            P.tdm[gi] = make_float4(health[s], __int_as_float(cd_atk[s]), __int_as_float(cd_mov[s]),
-                                    __int_as_float((now_alive[s] ? 1 : 0) | (hits[s] << 8)));
-            S.ang()[i] = ang[s];
-        }
+        if (TDM) P.tdm[gi] = make_float4(health[s], __int_as_float(cd_atk[s]), __int_as_float(cd_mov[s]),
+                                         __int_as_float((now_alive[s] ? 1 : 0) | (hits[s] << 8)));
     }
 
     {
         const bool oc = g.ballot(overflow_c) != 0, ot = g.ballot(overflow_t) != 0;
+        eflags = (eflags & ~MACM_ENV_FRESH) | (oc ? MACM_ENV_CONTACT_OVERFLOW : 0) | (ot ? MACM_ENV_TOUCH_OVERFLOW : 0);
+        step_cnt = step;
         if (g.gl == 0) {
-            const int flags = (es.y & ~MACM_ENV_FRESH) | (oc ? MACM_ENV_CONTACT_OVERFLOW : 0) |
-                              (ot ? MACM_ENV_TOUCH_OVERFLOW : 0);
-            P.c_cnt[env] = cnt;
-            P.done[env] = (uint8_t)done;
-            P.env_state[env] = make_int4(step, flags, tc, winner);
+            if (R.done()) R.done()[(size_t)ks * P.E + env] = (uint8_t)done;
+            if (last) {
+                P.c_cnt[env] = cnt;
+                P.done[env] = (uint8_t)done;
+                P.env_state[env] = make_int4(step, eflags, tc, winner);
+            }
         }
+    }
+    if (TDM) {
+#pragma unroll
+        for (int s = 0; s < APL; ++s) was_alive[s] = now_alive[s];
     }
 
     PHASE_STAMP(11);
     // ---- phase 13: observations (mvmnt.py:181-222 / combat.py:206-227) ----------------------------
-    if (TDM) {
-        g.sync();
-        tdm_observe<G, APL>(g, S, P, env, alive);
-    } else {
-        flock_observe<G, APL>(g, S, P, env, ang);
+    // (a rollout without per-step observation arrays only observes after its last step)
+    if (last || R.obs() || R.policy() == MACM_BOT_FLOCK) {
+        float* ob_k = R.obs() ? R.obs() + (size_t)ks * EN * P.obs_dim : nullptr;
+        if (TDM) {
+            g.sync();
+            tdm_observe<G, APL>(g, S, P, env, alive, last ? P.obs : ob_k, last ? ob_k : nullptr);
+        } else {
+            int* nn_k = R.nn_idx() ? R.nn_idx() + (size_t)ks * EN : nullptr;
+            float2* tgo = (R.policy() == MACM_BOT_FLOCK && !last) ? reinterpret_cast<float2*>(S.nw()) : nullptr;
+            flock_observe<G, APL>(g, S, P, env, ang, last ? P.obs : ob_k, last ? P.nn_idx : nn_k, last ? ob_k : nullptr,
+                                  last ? nn_k : nullptr, tgo);
+        }
     }
     PHASE_STAMP(12);
+    }   // for ks
 #ifndef MACM_PHASE_TRACE
     if (P.trace && g.gl == 0) {   // macm_set_trace: per-env timing record
         unsigned long long t1, smid;
@@ -1581,8 +1698,8 @@ __global__ void __launch_bounds__(128) macm_observe_kernel(const __grid_constant
         if (s == 0) alive.x = bm; else alive.y = bm;
     }
     g.sync();
-    if (KIND == MACM_ENV_TDM) tdm_observe<G, APL>(g, S, P, env, alive);
-    else flock_observe<G, APL>(g, S, P, env, ang);
+    if (KIND == MACM_ENV_TDM) tdm_observe<G, APL>(g, S, P, env, alive, P.obs, nullptr);
+    else flock_observe<G, APL>(g, S, P, env, ang, P.obs, P.nn_idx, nullptr, nullptr);
 }
 
 // Body creation for every agent (mvmnt.py:61-76): fat AABB = tight +- b2_aabbExtension, awake,
@@ -1611,7 +1728,8 @@ __global__ void macm_reset_kernel(const __grid_constant__ SimConst P)
 }
 
 template <int G, int APL, int KIND>
-cudaError_t launch_one(const SimConst& P, const LaunchCfg& cfg, const void* actions, cudaStream_t s, bool observe_only)
+cudaError_t launch_one(const SimConst& P, const LaunchCfg& cfg, const void* actions, const Rollout& R, cudaStream_t s,
+                       bool observe_only)
 {
     if (observe_only) {
         macm_observe_kernel<G, APL, KIND><<<cfg.obs_blocks, 128, cfg.obs_smem_bytes, s>>>(P);
@@ -1629,19 +1747,23 @@ cudaError_t launch_one(const SimConst& P, const LaunchCfg& cfg, const void* acti
     at[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = at;
     lc.numAttrs = 1;
-    return cudaLaunchKernelEx(&lc, macm_step_kernel<G, APL, KIND>, P, actions);
+    if (R.K == 1 && R.policy < 0 && !R.obs && !R.nn_idx && !R.rewards && !R.collided && !R.done)
+        return cudaLaunchKernelEx(&lc, macm_step_kernel<G, APL, KIND, false>, P, actions, R);
+    return cudaLaunchKernelEx(&lc, macm_step_kernel<G, APL, KIND, true>, P, actions, R);
 }
 
 template <int G, int APL, int KIND>
 cudaError_t prepare_one(const LaunchCfg& cfg, int* blocks_per_sm)
 {
-    cudaError_t e = cudaFuncSetAttribute(macm_step_kernel<G, APL, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(macm_step_kernel<G, APL, KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          cfg.smem_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(macm_step_kernel<G, APL, KIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.smem_bytes);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(macm_observe_kernel<G, APL, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              cfg.obs_smem_bytes);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, macm_step_kernel<G, APL, KIND>, cfg.threads,
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, macm_step_kernel<G, APL, KIND, false>, cfg.threads,
                                                          cfg.smem_bytes);
 }
 
@@ -1719,16 +1841,16 @@ cudaError_t macm_prepare_kernels(const SimConst& P, const LaunchCfg& cfg, int* b
 #undef CALL
 }
 
-cudaError_t macm_launch_step(const SimConst& P, const LaunchCfg& cfg, const void* actions, cudaStream_t s)
+cudaError_t macm_launch_step(const SimConst& P, const LaunchCfg& cfg, const void* actions, const Rollout& R, cudaStream_t s)
 {
-#define CALL(G_, A_, K_) launch_one<G_, A_, K_>(P, cfg, actions, s, false)
+#define CALL(G_, A_, K_) launch_one<G_, A_, K_>(P, cfg, actions, R, s, false)
     DISPATCH_SHAPE(CALL)
 #undef CALL
 }
 
 cudaError_t macm_launch_observe(const SimConst& P, const LaunchCfg& cfg, cudaStream_t s)
 {
-#define CALL(G_, A_, K_) launch_one<G_, A_, K_>(P, cfg, nullptr, s, true)
+#define CALL(G_, A_, K_) launch_one<G_, A_, K_>(P, cfg, nullptr, Rollout{}, s, true)
     DISPATCH_SHAPE(CALL)
 #undef CALL
 }

@@ -51,16 +51,54 @@ struct SimConst {
     unsigned long long* trace;  // [E,4] per-env timing record (macm_set_trace), or null
 };
 
+// Arguments of a multi-step launch (macm_rollout): K consecutive steps of every env inside one kernel, the env's
+// state staying on chip between them.  Per-step outputs go to the caller's [K, ...] arrays (any of them may be
+// null); the sim's bound output buffers receive the last step's values, exactly as after K calls of macm_step.
+struct Rollout {
+    int K;              // steps in this launch (macm_step: 1)
+    int sync;           // experiment: block barrier every `sync` steps (0 = never)
+    int policy;         // MACM_BOT_* when `actions` is null (the actions=None mode of mvmnt.py:86-92), else -1
+    unsigned long long seed;
+    float* obs; int* nn_idx; float* rewards; uint8_t* collided; uint8_t* done;
+};
+
 struct LaunchCfg {
     int G, APL, envs_per_block, threads, blocks, smem_bytes;   // the step kernel
     int per_env_bytes;                                          // shared memory of one env
     int obs_blocks, obs_smem_bytes;                             // get_obs alone: always 128-thread blocks
 };
 
+#ifdef __CUDACC__
+// Philox4x32-10 (Salmon et al., SC'11): counter-based, so a draw is a pure function of
+// (seed, index, stream) and does not depend on launch geometry.
+struct Philox {
+    uint32_t c[4];
+    __device__ Philox(uint64_t seed, uint64_t index, uint32_t stream, uint32_t sub)
+    {
+        uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+        c[0] = (uint32_t)index; c[1] = (uint32_t)(index >> 32); c[2] = stream; c[3] = sub;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+            const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+            c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+            k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+        }
+    }
+    // 53-bit uniform in [0, 1), the construction CPython's random.random() uses
+    __device__ double u53(int pair) const
+    {
+        const uint32_t a = c[pair * 2] >> 5, b = c[pair * 2 + 1] >> 6;
+        return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
+    }
+};
+#endif
+
 // implemented in macm_kernels.cu
 cudaError_t macm_launch_cfg(const SimConst& P, int sm_count, LaunchCfg* cfg);
 cudaError_t macm_prepare_kernels(const SimConst& P, const LaunchCfg& cfg, int* blocks_per_sm);
-cudaError_t macm_launch_step(const SimConst& P, const LaunchCfg& cfg, const void* actions, cudaStream_t s);
+cudaError_t macm_launch_step(const SimConst& P, const LaunchCfg& cfg, const void* actions, const Rollout& R, cudaStream_t s);
 cudaError_t macm_launch_observe(const SimConst& P, const LaunchCfg& cfg, cudaStream_t s);
 cudaError_t macm_launch_reset(const SimConst& P, cudaStream_t s);
 cudaError_t macm_launch_sample(const SimConst& P, uint64_t seed, double start_spread, double start_x, double start_y,

@@ -55,9 +55,13 @@ class MacmLaunchInfo(C.Structure):
                [(n, C.c_float) for n in ("dt", "dt_ratio", "inv_mass", "damping_factor", "binary_d2_threshold")]
 
 
+class MacmRolloutOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("obs", "nn_idx", "rewards", "collided", "done")]
+
+
 EXPORTS = ("macm_abi_version", "macm_strerror", "macm_last_cuda_error", "macm_params_default", "macm_create",
            "macm_destroy", "macm_get_buffer_sizes", "macm_get_launch_info", "macm_bind", "macm_reset",
-           "macm_sample_reset", "macm_step", "macm_observe", "macm_bot_actions", "macm_step_host", "macm_step_host_async", "macm_host_sync",
+           "macm_sample_reset", "macm_step", "macm_rollout", "macm_observe", "macm_bot_actions", "macm_step_host", "macm_step_host_async", "macm_host_sync",
            "macm_host_alloc",
            "macm_host_free", "macm_launch_count", "macm_set_trace")
 
@@ -92,6 +96,7 @@ def lib():
         L.macm_reset.argtypes = [vp, vp]
         L.macm_sample_reset.argtypes = [vp, u64, vp]
         L.macm_step.argtypes = [vp, vp, vp]
+        L.macm_rollout.argtypes = [vp, vp, C.c_int32, C.c_int32, u64, C.POINTER(MacmRolloutOut), vp]
         L.macm_observe.argtypes = [vp, vp]
         L.macm_bot_actions.argtypes = [vp, C.c_int, u64, vp, vp]
         L.macm_step_host.argtypes = [vp] * 7
@@ -102,7 +107,7 @@ def lib():
         L.macm_launch_count.restype = C.c_int64
         L.macm_launch_count.argtypes = [vp]
         L.macm_set_trace.argtypes = [vp, vp]
-        if L.macm_abi_version() != 1:
+        if L.macm_abi_version() != 2:
             raise MacmError("libmacm.so ABI version mismatch")
         _lib = L
     return _lib

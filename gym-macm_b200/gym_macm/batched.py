@@ -150,6 +150,23 @@ class Engine(object):
     def step(self, actions):
         _lib.check(_lib.lib().macm_step(self._h, C.c_void_p(actions.data_ptr()), self._stream()), self._h)
 
+    def rollout(self, actions, n_steps, policy=None, seed=0, out=None):
+        """macm_rollout: `n_steps` steps in one launch.  `actions` is a device tensor with a leading step
+        axis, or None with `policy` = a _lib.BOTS code (the actions=None mode).  `out` maps any of
+        obs / nn_idx / rewards / collided / done to a device tensor with a leading step axis."""
+        ro = _lib.MacmRolloutOut()
+        for name, ten in (out or {}).items():
+            setattr(ro, name, ten.data_ptr())
+        ptr = C.c_void_p(actions.data_ptr()) if actions is not None else None
+        _lib.check(_lib.lib().macm_rollout(self._h, ptr, int(n_steps), -1 if policy is None else int(policy),
+                                           C.c_uint64(int(seed) & (2 ** 64 - 1)), C.byref(ro), self._stream()), self._h)
+
+    def rollout_buffers(self, n_steps, want=("obs", "nn_idx", "rewards", "collided", "done")):
+        """Device tensors for the per-step outputs of rollout(): the bound output buffers with a leading step axis."""
+        torch = _torch()
+        return {n: torch.empty((int(n_steps),) + tuple(self.t[n].shape), dtype=self.t[n].dtype, device=self.device)
+                for n in want if n in self.t}
+
     def observe(self):
         _lib.check(_lib.lib().macm_observe(self._h, self._stream()), self._h)
 
@@ -315,6 +332,42 @@ class BatchedFlock(object):
         self.engine.step(a)
         return self.obs, self.engine.t["rewards"]
 
+    def rollout(self, actions=None, n_steps=None, policy="random", seed=0, want=("obs", "nn_idx", "rewards", "collided", "done"),
+                out=None):
+        """`n_steps` consecutive steps in one kernel launch (macm_rollout) -- the reference's
+        `for _ in range(n_steps): obs, rewards = env.step(a_k)` loop (README.md:8-14) with every env's bodies
+        held on chip between its steps; bit-identical to calling step() n_steps times.
+
+        actions: uint8 [K,E,N,4] on the device (continuous mode: float32 [K,E,N,2]), or None for the
+        reference's actions=None mode (mvmnt.py:86-92) with every agent driven by the scripted actor `policy`
+        (test_scripts/bots.py).  Returns a dict of per-step tensors (leading axis K) for the names in `want`;
+        with "obs" left out the observation pass only runs after the last step (action repeat).  The usual
+        attributes (obs, rewards, done, state) hold the last step's values afterwards."""
+        torch = _torch()
+        E, N = self.engine.E, self.engine.N
+        if actions is not None:
+            a = actions
+            if self.settings.action_mode == "discrete":
+                if not (torch.is_tensor(a) and a.dtype == torch.uint8 and a.is_cuda and a.dim() == 4 and
+                        tuple(a.shape[1:]) == (E, N, 4) and a.is_contiguous()):
+                    a3 = torch.as_tensor(a, device=self.device)
+                    a = torch.zeros((a3.shape[0], E, N, 4), dtype=torch.uint8, device=self.device)
+                    a[..., 0:a3.shape[-1]] = a3.reshape(a3.shape[0], E, N, -1)
+            else:
+                a = torch.as_tensor(a, dtype=torch.float32, device=self.device).reshape(-1, E, N, 2).contiguous()
+            K = int(a.shape[0]) if n_steps is None else int(n_steps)
+            if K > a.shape[0]:
+                raise ValueError("n_steps exceeds the leading axis of actions")
+            pol = None
+        else:
+            if n_steps is None:
+                raise ValueError("n_steps is required with actions=None")
+            a, K, pol = None, int(n_steps), _lib.BOTS[policy]
+        if out is None:
+            out = self.engine.rollout_buffers(K, want)
+        self.engine.rollout(a, K, pol, seed, out)
+        return out
+
     def step_host(self, actions):
         """Same step through the host-buffer entry point (macm_step_host): `actions` is a CPU
         uint8 [E,N,4] / float32 [E,N,2] tensor; returns pinned CPU tensors."""
@@ -458,6 +511,7 @@ class BatchedTDM(object):
         return out
 
     contacts = BatchedFlock.contacts
+    rollout = BatchedFlock.rollout
 
     def close(self):
         self.engine.close()

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MACM_ABI_VERSION 1
+#define MACM_ABI_VERSION 2
 #define MACM_MAX_AGENTS 64   /* per environment (contact adjacency is a 64-bit row per agent) */
 #define MACM_MAX_TARGETS 16
 #define MACM_MAX_TEAMS 8
@@ -195,6 +195,30 @@ int macm_sample_reset(macm_sim* sim, uint64_t seed, void* stream);
  * actions (device): discrete uint8 [E,N,4] = a0 a1 a2 a3 (a3: TDM attack bit; Flock ignores it),
  *                   continuous float [E,N,2]. */
 int macm_step(macm_sim* sim, const void* actions, void* stream);
+
+/* Per-step outputs of macm_rollout: caller-owned device arrays with a leading step axis; any member may be NULL. */
+typedef struct macm_rollout_out {
+    float* obs;        /* [K,E,N,obs_dim]  16-byte aligned */
+    int32_t* nn_idx;   /* [K,E,N]          (Flock) */
+    float* rewards;    /* [K,E,N] */
+    uint8_t* collided; /* [K,E,N] */
+    uint8_t* done;     /* [K,E] */
+} macm_rollout_out;
+
+/* n_steps consecutive Flock.step / TDM.step calls for every env in ONE launch -- the reference's
+ * `for _ in range(n_steps): obs, rewards = env.step(actions_k)` loop (README.md:8-14).  Every env runs its
+ * n_steps steps back to back with its bodies, fat AABBs and clocks held on chip; only the actions (in), the
+ * per-step outputs (out) and the contact lists touch HBM between the steps.  Bit-identical to n_steps calls
+ * of macm_step: the bound state and output buffers end up exactly as after the last of those calls, and
+ * out->x[k] holds what buffer x held after call k.
+ *   actions != NULL : [n_steps,E,N,4] uint8 (discrete) or [n_steps,E,N,2] float (continuous), device.
+ *   actions == NULL : the actions=None mode (mvmnt.py:86-92): every agent's actor picks its action from
+ *                     its own last observation, policy = MACM_BOT_IDLE..MACM_BOT_RANDOM as in macm_bot_actions
+ *                     (MACM_BOT_FLOCK: Flock with polar coordinates), draws keyed by (seed, env, agent, step_count).
+ * With out == NULL or out->obs == NULL the observation pass only runs after the last step (action repeat /
+ * frame skip); rewards of the intermediate steps are still available through out->rewards. */
+int macm_rollout(macm_sim* sim, const void* actions, int32_t n_steps, int32_t policy, uint64_t seed,
+                 const macm_rollout_out* out, void* stream);
 
 /* get_obs() alone on the current state (mvmnt.py:181-222 / combat.py:206-227). */
 int macm_observe(macm_sim* sim, void* stream);
