@@ -41,47 +41,85 @@ def measured_peak():
         return 6650.0, "fallback"
 
 
+_NVML_SAMPLER = r"""
+import sys, time
+import pynvml as N
+N.nvmlInit()
+h = N.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+get = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+while True:
+    sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+    r = get(h)
+    sys.stdout.write("%.6f,%d,%d,%d\n" % (time.time(), sm, mx, r))
+    sys.stdout.flush()
+    time.sleep(0.001)
+"""
+
+
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """SM clock and throttle reasons while the timed region runs: an NVML poller in its own process (about one
+    sample per millisecond, no GIL shared with the launch loop); `nvidia-smi -lms` when pynvml is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+            0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
-            self.th.start()
-        except Exception:
-            self.proc = None
+        self.rows, self.proc, self.kind = [], None, None
+        for kind, cmd in (("nvml", [sys.executable, "-c", _NVML_SAMPLER, str(index)]),
+                          ("nvidia-smi", ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "20"])):
+            try:
+                self.proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.kind = kind
+                self.th = threading.Thread(target=self._read, daemon=True)
+                self.th.start()
+                t_end = time.time() + 5.0          # wait for the first sample (NVML init)
+                while not self.rows and self.proc.poll() is None and time.time() < t_end:
+                    time.sleep(0.01)
+                if self.rows:
+                    break
+                self.proc.kill()
+                self.proc = None
+            except Exception:
+                self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows]
-        sm, mx, reasons = [], None, set()
+    def _parse(self, t_host, line):
+        f = [x.strip() for x in line.split(",")]
+        if self.kind == "nvml":
+            bits = int(f[3])
+            return float(f[0]), float(f[1]), float(f[2]), [nm for b, nm in self.BITS.items() if bits & b]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            f = [x.strip() for x in r.split(",")]
+        return t_host, float(f[0]), float(f[1]), [nm for nm, v in zip(names, f[3:7]) if v.lower().startswith("active")]
+
+    def stop(self, t0, t1):
+        """Samples taken inside [t0, t1]; if the region was too short to hold three of them, the nearest ones
+        taken under the same load (the warm-up steps run right before it) are added and counted separately."""
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock sampler available"], "samples": 0}
+        time.sleep(0.03)
+        self.proc.kill()
+        got = []
+        for th, line in list(self.rows):
             try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
+                got.append(self._parse(th, line))
             except Exception:
                 continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        inside = [g for g in got if t0 <= g[0] <= t1]
+        near = []
+        if len(inside) < 3:
+            near = sorted((g for g in got if g not in inside and t0 - 0.25 <= g[0] <= t1 + 0.002), key=lambda g: -g[0])[:8]
+        use = inside + near
+        reasons = sorted(set(r for g in use for r in g[3]))
+        return {"sm_mhz": statistics.median([g[1] for g in use]) if use else None,
+                "sm_max_mhz": use[0][2] if use else None, "reasons": reasons, "samples": len(inside),
+                "samples_warmup": len(near), "sampler": self.kind}
 
 
 def b_alg_per_agent_step(c_bar, T, N):
@@ -159,11 +197,14 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rot", type=int, default=16, help="independent batches rotated through (L2 eviction)")
     ap.add_argument("--envs", type=int, default=N_ENVS)
+    ap.add_argument("--rollout", type=int, default=32, help="steps per launch of the macm_rollout leg (0 = skip it)")
+    ap.add_argument("--streams", type=int, default=1,
+                    help="streams the independent batches of the rotation are spread over (a batch keeps its stream)")
     ap.add_argument("--gather", action="store_true", help="NCCL all-gather of obs+rewards every step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--e2e-steps", type=int, default=60)
@@ -204,6 +245,7 @@ def main():
             os.dup2(keep, 1)
             os.close(keep)
     E, N, ROT = args.envs, N_AGENTS, args.rot
+    sampler = ClockSampler(local) if rank == 0 else None   # started early: it is warm when the timed region begins
 
     extra = {"max_touching": args.max_touching} if args.max_touching else {}
     sims = [gym_macm.BatchedFlock(E, n_agents=[N], reward_mode="linear", device=dev, seed=1234 + 1000 * rank + r, **extra)
@@ -222,15 +264,21 @@ def main():
                     for k in ("obs", "rewards")]
         gstream = torch.cuda.Stream(device=dev)
 
+    main_stream = torch.cuda.current_stream(dev)
+    NS = max(1, min(args.streams, ROT))
+    streams = [torch.cuda.Stream(device=dev) for _ in range(NS)] if NS > 1 else [None]
+
     def one_step(k):
         s = sims[k % ROT]
+        st = streams[(k % ROT) % NS]
         if args.policy == "flock":
-            a = s.bot_actions("flock")
+            with torch.cuda.stream(st if st is not None else main_stream):
+                a = s.bot_actions("flock")
         else:
             a = acts[(k // ROT + 7 * (k % ROT)) % POOL]
-        s.engine.step(a)
+        s.engine.step(a, st)
         if gathered is not None:
-            gstream.wait_stream(torch.cuda.current_stream(dev))
+            gstream.wait_stream(st if st is not None else main_stream)
             with torch.cuda.stream(gstream):
                 dist.all_gather_into_tensor(gathered[0], s.state["obs"])
                 dist.all_gather_into_tensor(gathered[1], s.state["rewards"])
@@ -245,13 +293,18 @@ def main():
     if world > 1:
         dist.barrier()
     launches0 = sum(s.engine.launch_count for s in sims)
-    sampler = ClockSampler(local) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t0 = time.time()
     ev0.record()
+    for st in streams:
+        if st is not None:
+            st.wait_stream(main_stream)      # every stream starts after the start event ...
     for k in range(args.steps):
         one_step(k)
+    for st in streams:
+        if st is not None:
+            main_stream.wait_stream(st)      # ... and the stop event waits for all of them
     if gstream is not None:
         torch.cuda.current_stream(dev).wait_stream(gstream)   # the last gathers are part of the timed region
     ev1.record()
@@ -267,6 +320,61 @@ def main():
     clocks = sampler.stop(t0, t1) if sampler else None
     ms_per_step = ms / args.steps
     value = world * E * N * args.steps / (ms * 1e-3)
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    # ---- two further legs, reported beside the headline (same workload, same batches, device-timed) -----
+    # (1) the independent batches of the rotation spread over two streams: one batch's tail (a few envs with
+    #     long islands finishing alone) overlaps the next batch's body.  What a rollout worker with several
+    #     env batches in flight gets.
+    legs = {}
+    if NS == 1 and ROT >= 2 and gathered is None and args.policy == "random":
+        st2 = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        for rep_ in range(2):      # first pass = warm-up
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for st in st2:
+                st.wait_stream(main_stream)
+            for k in range(args.steps):
+                sims[k % ROT].engine.step(acts[(k // ROT + 7 * (k % ROT)) % POOL], st2[(k % ROT) & 1])
+            for st in st2:
+                main_stream.wait_stream(st)
+            a1.record()
+            torch.cuda.synchronize()
+        ms2 = max_over_ranks(a0.elapsed_time(a1))
+        legs["two_streams"] = {"value": world * E * N * args.steps / (ms2 * 1e-3), "unit": UNIT,
+                                "ms_per_step": ms2 / args.steps, "steps": args.steps,
+                                "note": "same steps, the rotation's batches alternating between two streams"}
+    # (2) macm_rollout: R steps of a batch per launch, the envs' bodies held on chip between the steps; every
+    #     step still writes its obs / nn_idx / rewards / collided / done (to per-step arrays).
+    if gathered is None and args.policy == "random" and args.rollout > 0:
+        R = min(args.rollout, POOL)
+        outs = [sims[0].engine.rollout_buffers(R) for _ in range(2)]
+        n_launch = max(ROT, (args.steps // R) // ROT * ROT)
+        for rep_ in range(2):
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for j in range(n_launch):
+                sims[j % ROT].engine.rollout(acts[:R], R, None, 0, outs[j & 1])
+            a1.record()
+            torch.cuda.synchronize()
+        msr = max_over_ranks(a0.elapsed_time(a1))
+        legs["rollout"] = {"value": world * E * N * n_launch * R / (msr * 1e-3), "unit": UNIT,
+                            "ms_per_step": msr / (n_launch * R), "steps_per_launch": R, "launches": n_launch,
+                            "note": "macm_rollout, per-step outputs written every step; bit-identical to single steps "
+                                    "(tests/test_gpu_rollout.py)"}
+        del outs
 
     # live contacts per agent (c-bar of the roofline formula), measured on this rank's batches
     c_bar = float(sum(float(s.state["contact_count"].sum()) for s in sims) / (ROT * E * N))
@@ -343,6 +451,7 @@ def main():
                        "actions": "pre-generated on device, U{0,1,2}^3" if args.policy == "random" else "bots.flock on device",
                        "l2": "inputs larger than L2: rotation over %d independent batches (%.0f MB of state+outputs)"
                              % (ROT, ROT * E * N * 73 / 1e6),
+                       "streams": NS,
                        "parallelism": "envs sharded, %d per GPU, no data-path collective%s" % (
                            E, " + NCCL all-gather of obs/rewards" if gathered is not None else ""),
                        "launch": {"lanes_per_env": info.lanes_per_env, "agents_per_lane": info.agents_per_lane,
@@ -356,6 +465,7 @@ def main():
                          "kernel": "macm_flock_step_kernel<32,2>", "kernel_ms": ms_per_step},
             "cpu_baseline": cpu,
         }
+        out.update(legs)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -138,7 +138,9 @@ class Engine(object):
         except Exception:
             pass
 
-    def _stream(self):
+    def _stream(self, stream=None):
+        if stream is not None:
+            return C.c_void_p(stream.cuda_stream)
         return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
 
     def reset(self):
@@ -147,10 +149,12 @@ class Engine(object):
     def sample_reset(self, seed):
         _lib.check(_lib.lib().macm_sample_reset(self._h, C.c_uint64(int(seed) & (2 ** 64 - 1)), self._stream()), self._h)
 
-    def step(self, actions):
-        _lib.check(_lib.lib().macm_step(self._h, C.c_void_p(actions.data_ptr()), self._stream()), self._h)
+    def step(self, actions, stream=None):
+        """One step on torch's current stream, or on `stream` (a torch.cuda.Stream): independent batches stepped
+        on different streams overlap on the device."""
+        _lib.check(_lib.lib().macm_step(self._h, C.c_void_p(actions.data_ptr()), self._stream(stream)), self._h)
 
-    def rollout(self, actions, n_steps, policy=None, seed=0, out=None):
+    def rollout(self, actions, n_steps, policy=None, seed=0, out=None, stream=None):
         """macm_rollout: `n_steps` steps in one launch.  `actions` is a device tensor with a leading step
         axis, or None with `policy` = a _lib.BOTS code (the actions=None mode).  `out` maps any of
         obs / nn_idx / rewards / collided / done to a device tensor with a leading step axis."""
@@ -159,7 +163,7 @@ class Engine(object):
             setattr(ro, name, ten.data_ptr())
         ptr = C.c_void_p(actions.data_ptr()) if actions is not None else None
         _lib.check(_lib.lib().macm_rollout(self._h, ptr, int(n_steps), -1 if policy is None else int(policy),
-                                           C.c_uint64(int(seed) & (2 ** 64 - 1)), C.byref(ro), self._stream()), self._h)
+                                           C.c_uint64(int(seed) & (2 ** 64 - 1)), C.byref(ro), self._stream(stream)), self._h)
 
     def rollout_buffers(self, n_steps, want=("obs", "nn_idx", "rewards", "collided", "done")):
         """Device tensors for the per-step outputs of rollout(): the bound output buffers with a leading step axis."""

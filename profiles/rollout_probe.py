@@ -28,7 +28,8 @@ for r, s in enumerate(sims):
     s.rollout(acts[r:r + SETTLE], want=())
 torch.cuda.synchronize()
 for K in Ks:
-    outs = [s.engine.rollout_buffers(K) for s in sims[:2]]   # two sets in alternation (the consumer double-buffers)
+    want = tuple(w for w in os.environ.get("WANT", "obs,nn_idx,rewards,collided,done").split(",") if w)
+    outs = [s.engine.rollout_buffers(K, want) for s in sims[:2]]   # two sets in alternation (the consumer double-buffers)
     launches = max(4 * ROT, (2048 // K) // ROT * ROT)
     for rep in range(2):
         torch.cuda.synchronize()
@@ -40,6 +41,6 @@ for K in Ks:
         e1.record()
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / (launches * K)
-    print(json.dumps({"envs": E, "steps_per_launch": K, "launches": launches, "us_per_step": 1e3 * ms,
+    print(json.dumps({"envs": E, "steps_per_launch": K, "want": list(want), "sync": os.environ.get("MACM_ROLLOUT_SYNC", "default"), "launches": launches, "us_per_step": 1e3 * ms,
                       "agent_steps_per_sec": E * N / (ms * 1e-3)}), flush=True)
     del outs
