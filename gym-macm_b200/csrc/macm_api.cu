@@ -119,6 +119,12 @@ static int derive_constants(macm_sim* sim)
     int TC = p.max_touching > 0 ? p.max_touching : (C < 2 * p.n_agents ? C : 2 * p.n_agents);
     if (TC > C) TC = C;
     TC = (TC + 15) / 16 * 16;
+    // macm_rollout parks 20 bytes per agent slot in the (24-byte-per-entry) touching-contact stage between steps
+    {
+        const int slots = p.n_agents > 32 ? 64 : (p.n_agents > 16 ? 32 : 16);
+        const int need = (20 * slots + 23) / 24;
+        if (TC < need) TC = (need + 15) / 16 * 16;
+    }
     if (TC > 240) TC = 240;  // levels are bytes; the DFS keeps one taken-bit per chunk of G contacts
     K.C = C; K.TC = TC;
     K.kind = p.env_kind; K.reward_mode = p.reward_mode; K.action_mode = p.action_mode; K.coord = p.coord;

@@ -849,7 +849,7 @@ __device__ __noinline__ int fresh_world_contacts(const Grp<G>& g, const EnvS<G *
 // The scripted actors of test_scripts/bots.py inside a rollout (the actions=None mode of mvmnt.py:86-92):
 // the same rules and the same counter-based draws as macm_bot_kernel (macm_aux.cu).  tn = the agent's target
 // node (r, theta) of the last observation.
-__device__ __forceinline__ uint32_t bot_action(const SimConst& P, const Rollout& R, float2 tn, int env, int i, int step)
+__device__ __noinline__ uint32_t bot_action(const SimConst& P, const Rollout& R, float2 tn, int env, int i, int step)
 {
     uint32_t a0 = 1, a1 = 1, a2 = 1, a3 = 0;
     switch (R.policy) {
@@ -1039,6 +1039,11 @@ __global__ void __launch_bounds__((G == 32 ? MACM_WIDE_THREADS : 128), (G == 32 
     for (int s = 0; s < APL; ++s) {
         const int i = g.gl + s * G;
         const size_t gi = (size_t)env * N + (valid[s] ? i : 0);
+        if (ROLL && ks > 0) {   // parked before the previous step's observation pass (see there)
+            v[s] = vel[i];
+            fatr[s] = reinterpret_cast<const float4*>(S.t_n())[i];
+            slp[s] = reinterpret_cast<const float*>(reinterpret_cast<const float4*>(S.t_n()) + NC)[i];
+        }
         pos[i] = c[s];
         fat[i] = fatr[s];
         adj[i] = make_uint2(0u, 0u);
@@ -1636,6 +1641,19 @@ __global__ void __launch_bounds__((G == 32 ? MACM_WIDE_THREADS : 128), (G == 32 
 
     PHASE_STAMP(11);
     // ---- phase 13: observations (mvmnt.py:181-222 / combat.py:206-227) ----------------------------
+    // Between two steps of a rollout the velocities, fat AABBs and sleep timers wait in shared memory (the
+    // velocity array and the touching-contact stage, both idle until the next step's phase 2), so that the
+    // nearest-agent search -- the register-hungriest phase -- does not have to carry them.
+    if (ROLL && !last) {
+        g.sync();
+#pragma unroll
+        for (int s = 0; s < APL; ++s) {
+            const int i = g.gl + s * G;
+            vel[i] = v[s];
+            reinterpret_cast<float4*>(S.t_n())[i] = fatr[s];
+            reinterpret_cast<float*>(reinterpret_cast<float4*>(S.t_n()) + NC)[i] = slp[s];
+        }
+    }
     // (a rollout without per-step observation arrays only observes after its last step)
     if (last || R.obs() || R.policy() == MACM_BOT_FLOCK) {
         float* ob_k = R.obs() ? R.obs() + (size_t)ks * EN * P.obs_dim : nullptr;
@@ -1794,7 +1812,7 @@ cudaError_t macm_launch_cfg(const SimConst& P, int sm_count, LaunchCfg* cfg)
     }
     if (const char* e = getenv("MACM_BLOCK_THREADS")) {   // experiments (profiles/README.md): 128 or 896
         const int t = atoi(e);
-        if (t == 128 || (t == MACM_WIDE_THREADS && gpw == 1)) cfg->threads = t;
+        if (t == 128 || (gpw == 1 && t > 128 && t <= MACM_WIDE_THREADS && t % 32 == 0)) cfg->threads = t;
     }
     cfg->envs_per_block = (cfg->threads / 32) * gpw;
     cfg->blocks = (P.E + cfg->envs_per_block - 1) / cfg->envs_per_block;
