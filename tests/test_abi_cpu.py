@@ -43,6 +43,9 @@ def test_struct_layout_matches_header(built):
     body = hdr[hdr.index("typedef struct macm_buffers {"):hdr.index("} macm_buffers;")]
     names = re.findall(r"^\s*(?:float|uint32_t|int32_t|uint8_t)\*\s+(\w+);", body, re.M)
     assert tuple(names) == built.BUFFER_NAMES
+    body = hdr[hdr.index("typedef struct macm_rollout_out {"):hdr.index("} macm_rollout_out;")]
+    names = re.findall(r"^\s*(?:float|int32_t|uint8_t)\*\s+(\w+);", body, re.M)
+    assert names == [f[0] for f in built.MacmRolloutOut._fields_]
 
 
 def test_defaults_are_the_reference_settings(built):
