@@ -168,7 +168,9 @@ def run_reference(args, rank, world):
     from oracle import oracle
     oracle.build()
     cores = len(os.sched_getaffinity(0))
-    sample_envs = 256   # a bounded sample of the 4096-env batch per step
+    # a bounded sample of the 4096-env batch per step: 64 envs per host thread, so that starting and joining the
+    # worker threads (once per step) stays below a tenth of the step
+    sample_envs = min(N_ENVS, 64 * cores)
     rng = np.random.default_rng(1234)
     pos, ang, tg = random_state(rng, sample_envs, N_AGENTS, 1)
     ref = oracle.OracleBatch(sample_envs, n_agents=N_AGENTS, n_targets=1, reward_mode=1)
@@ -207,7 +209,7 @@ def main():
                     help="streams the independent batches of the rotation are spread over (a batch keeps its stream)")
     ap.add_argument("--gather", action="store_true", help="NCCL all-gather of obs+rewards every step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--e2e-steps", type=int, default=60)
+    ap.add_argument("--e2e-steps", type=int, default=240)
     ap.add_argument("--e2e-depth", type=int, default=3, help="independent batches in flight on the host-buffer path")
     ap.add_argument("--policy", default="random", choices=["random", "flock"])
     ap.add_argument("--settle", type=int, default=64, help="untimed steps per batch after the random spawn")
@@ -435,11 +437,14 @@ def main():
                 from oracle import oracle
                 oracle.build()
                 cores = len(os.sched_getaffinity(0))
-                n_envs = max(cores * 8, 64)
+                n_envs = min(N_ENVS, cores * 64)   # 64 envs per thread and step: thread start/join well amortised
                 rate, st, el = cpu_oracle_rate(n_envs, cores, args.cpu_seconds)
+                rate1, st1, el1 = cpu_oracle_rate(8, 1, min(3.0, args.cpu_seconds))   # single process, one thread
                 cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                        "sample": "%d envs x %d agents x %d steps in %.1f s; CPU restatement (oracle/), not pybox2d"
-                                 % (n_envs, N, st, el)}
+                                 % (n_envs, N, st, el),
+                       "single_thread": {"value": rate1, "unit": UNIT, "cores": 1,
+                                         "sample": "8 envs x %d agents x %d steps in %.1f s" % (N, st1, el1)}}
             except Exception as ex:  # the checker missing must not hide the GPU number
                 cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
         info = sims[0].engine.info
