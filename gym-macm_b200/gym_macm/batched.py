@@ -138,7 +138,10 @@ class Engine(object):
         except Exception:
             pass
 
+    stream = None   # a torch.cuda.Stream this engine enqueues on; None = torch's current stream at call time
+
     def _stream(self, stream=None):
+        stream = stream if stream is not None else self.stream
         if stream is not None:
             return C.c_void_p(stream.cuda_stream)
         return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
@@ -230,7 +233,8 @@ class BatchedFlock(object):
 
     name = "Flock v0 (batched)"
 
-    def __init__(self, n_envs, n_agents=[10], actors=None, colors=None, targets=None, device=None, seed=0, **kwargs):
+    def __init__(self, n_envs, n_agents=[10], actors=None, colors=None, targets=None, device=None, seed=0, stream=None,
+                 **kwargs):
         self.settings = flockSettings(**kwargs)
         self.n_agents = _as_list(n_agents)
         self.n_envs = int(n_envs)
@@ -245,10 +249,15 @@ class BatchedFlock(object):
             raise ValueError("targets must use the indices 0..T-1")
         self.actors, self.colors = actors, colors
         self.engine = Engine(flock_params(self.settings, self.n_envs, N, self.n_targets), device)
+        # Independent batches given a stream each overlap on the device (one batch's last envs finish while the
+        # next batch starts); with stream=None every call goes to torch's current stream.
+        self.engine.stream = stream
         torch = _torch()
         self.engine.t["target_idx"].copy_(torch.tensor(self.targets_idx, dtype=torch.uint8))
         self.agents = list(range(N))
         self._act4 = None
+        if stream is not None:   # the buffers were allocated and filled on torch's current stream
+            stream.wait_stream(torch.cuda.current_stream(self.device))
         if seed is not None:   # seed=None: the caller loads a state itself (load_state)
             self.reset(seed)
 
@@ -417,7 +426,7 @@ class BatchedTDM(object):
 
     name = "Team Deathmatch (batched)"
 
-    def __init__(self, n_envs, n_agents=[1, 1], actors=None, colors=None, device=None, seed=0, **kwargs):
+    def __init__(self, n_envs, n_agents=[1, 1], actors=None, colors=None, device=None, seed=0, stream=None, **kwargs):
         self.settings = combatSettings(**kwargs)
         self.n_agents = _as_list(n_agents)
         self.n_envs = int(n_envs)
@@ -428,10 +437,13 @@ class BatchedTDM(object):
             raise ValueError("at most 8 teams")
         self.actors, self.colors = actors, colors
         self.engine = Engine(tdm_params(self.settings, self.n_envs, N), device)
+        self.engine.stream = stream
         torch = _torch()
         self.engine.t["team"].copy_(torch.tensor(self.teams, dtype=torch.uint8))
         self.agents = list(range(N))
         self._act4 = None
+        if stream is not None:
+            stream.wait_stream(torch.cuda.current_stream(self.device))
         if seed is not None:
             self.reset(seed)
 

@@ -138,3 +138,25 @@ def test_tdm_dict_api_runs():
     assert env.done and (env.winner in (0, 1) or sum(env.n_alive) == 0 or env.time_passed > 60)
     assert set(rewards.values()) <= {0, -1}
     env.close()
+
+
+def test_batches_on_their_own_streams():
+    """Independent batches stepped on two streams (they overlap on the device) end up where serial stepping does."""
+    import torch
+    import gym_macm
+    E, N, K = 296, 64, 30
+    ss = [torch.cuda.Stream(device="cuda:0") for _ in range(2)]
+    serial = [gym_macm.BatchedFlock(E, n_agents=[N], device="cuda:0", seed=20 + r) for r in range(4)]
+    torch.cuda.synchronize()
+    par = [gym_macm.BatchedFlock(E, n_agents=[N], device="cuda:0", seed=20 + r, stream=ss[r & 1]) for r in range(4)]
+    acts = torch.zeros((K, E, N, 4), dtype=torch.uint8, device="cuda:0")
+    acts[..., :3] = torch.randint(0, 3, (K, E, N, 3), device="cuda:0", dtype=torch.uint8)
+    torch.cuda.synchronize()
+    for k in range(K):
+        for r in range(4):
+            serial[r].step(acts[(k + r) % K])
+            par[r].step(acts[(k + r) % K])
+    torch.cuda.synchronize()
+    for a, b in zip(serial, par):
+        for n in ("posvel", "angsleep", "fat", "obs", "nn_idx", "rewards", "contact_count"):
+            assert torch.equal(a.state[n], b.state[n]), n
