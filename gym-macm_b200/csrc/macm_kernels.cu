@@ -1442,7 +1442,6 @@ __global__ void __launch_bounds__((G == 32 ? MACM_WIDE_THREADS : 128), (G == 32 
             if (has) c_imp[S.t_slot()[g.gl]] = t_imp[g.gl];
         }
     }
-
     PHASE_STAMP(5);
     // ---- phase 6: integrate positions ------------------------------------------------------------
     float2 c0[APL];
