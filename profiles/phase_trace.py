@@ -68,3 +68,11 @@ if __name__ == "__main__":
             s_ = m & (tc == k)
             print("   tc=%d: envs %d  closure %.0f  DFS %.0f  lists %.0f  position %.0f" % (k, s_.sum(), (t[s_, 13] - t[s_, 4]).mean(),
                   (t[s_, 14] - t[s_, 13]).mean(), (t[s_, 5] - t[s_, 14]).mean(), d[s_, 7].mean()))
+    # the envs that set the kernel time: phase split of the 32 slowest
+    worst = np.argsort(-t[:, 12])[:32]
+    print("32 slowest envs: total %.0f  tc %.1f  multi %.2f" % (t[worst, 12].mean(), tc[worst].mean(), multi[worst].mean()))
+    for k, nm in enumerate(names):
+        print("   %-32s %9.0f" % (nm, d[worst, k].mean()))
+    print("   inside 4+5: closure %.0f  DFS %.0f  lists %.0f" % ((t[worst, 13] - t[worst, 4]).mean(), (t[worst, 14] - t[worst, 13]).mean(),
+                                                                  (t[worst, 5] - t[worst, 14]).mean()))
+    print("   tc of the 32 slowest:", sorted(tc[worst].tolist()))
