@@ -204,6 +204,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rot", type=int, default=16, help="independent batches rotated through (L2 eviction)")
     ap.add_argument("--envs", type=int, default=N_ENVS)
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the ranks to their GPU's NUMA node")
     ap.add_argument("--rollout", type=int, default=32, help="steps per launch of the macm_rollout leg (0 = skip it)")
     ap.add_argument("--streams", type=int, default=1,
                     help="streams the independent batches of the rotation are spread over (a batch keeps its stream)")
@@ -230,6 +231,10 @@ def main():
     import torch.distributed as dist
     import gym_macm
 
+    numa_cpus = None
+    if world > 1 and not args.no_numa:
+        from gym_macm.dist import bind_to_gpu_numa
+        numa_cpus = bind_to_gpu_numa(local)   # before any pinned allocation
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -456,7 +461,7 @@ def main():
                        "actions": "pre-generated on device, U{0,1,2}^3" if args.policy == "random" else "bots.flock on device",
                        "l2": "inputs larger than L2: rotation over %d independent batches (%.0f MB of state+outputs)"
                              % (ROT, ROT * E * N * 73 / 1e6),
-                       "streams": NS,
+                       "streams": NS, "numa_bound_cpus": len(numa_cpus) if numa_cpus else None,
                        "parallelism": "envs sharded, %d per GPU, no data-path collective%s" % (
                            E, " + NCCL all-gather of obs/rewards" if gathered is not None else ""),
                        "launch": {"lanes_per_env": info.lanes_per_env, "agents_per_lane": info.agents_per_lane,

@@ -882,7 +882,7 @@ __device__ __noinline__ uint32_t bot_action(const SimConst& P, const Rollout& R,
 // ROLL = false: one step per launch (macm_step); every rollout argument folds away at compile time.
 // ROLL = true: R.K steps per launch (macm_rollout), the env's bodies staying in registers / shared memory.
 template <int G, int APL, int KIND, bool ROLL>
-__global__ void __launch_bounds__((G == 32 ? MACM_WIDE_THREADS : 128), (G == 32 ? 1 : MACM_SMALL_BLOCKS)) macm_step_kernel(const __grid_constant__ SimConst P,
+__global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const __grid_constant__ SimConst P,
                                                         const void* __restrict__ actions,
                                                         const __grid_constant__ Rollout R_)
 {
@@ -1811,7 +1811,7 @@ cudaError_t macm_launch_cfg(const SimConst& P, int sm_count, LaunchCfg* cfg)
     }
     if (const char* e = getenv("MACM_BLOCK_THREADS")) {   // experiments (profiles/README.md): 128 or 896
         const int t = atoi(e);
-        if (t == 128 || (gpw == 1 && t > 128 && t <= MACM_WIDE_THREADS && t % 32 == 0)) cfg->threads = t;
+        if (t == 128 || (t > 128 && t <= MACM_WIDE_THREADS && t % 32 == 0)) cfg->threads = t;
     }
     cfg->envs_per_block = (cfg->threads / 32) * gpw;
     cfg->blocks = (P.E + cfg->envs_per_block - 1) / cfg->envs_per_block;

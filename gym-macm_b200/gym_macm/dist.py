@@ -11,6 +11,38 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa(local_rank):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers of the
+    host-stepping path (first touched here) and the DMA engines sit on the same socket.  Returns the CPU list it
+    bound to, or None when the box does not say (no NVML, a VM without NUMA topology): then nothing changes."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(local_rank))
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:      # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 def shard_range(n_total, rank, world):
     """Contiguous env range [start, start+count) of `rank`; the first n_total % world ranks get one more."""
     base, rem = divmod(int(n_total), int(world))

@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.join(ROOT, "gym-macm_b200"))
 import gym_macm
 
 dev = torch.device("cuda", 0)
-E, N, SETTLE, ROT = int(os.environ.get("ENVS", 4096)), 64, 64, 16
+E, N, SETTLE, ROT = int(os.environ.get("ENVS", 4096)), int(os.environ.get("AGENTS", 64)), 64, 16
 Ks = [int(x) for x in sys.argv[1:]] or [1, 2, 4, 8, 16, 32, 64]
 KMAX = max(Ks + [SETTLE])
 sims = [gym_macm.BatchedFlock(E, n_agents=[N], reward_mode="linear", device=dev, seed=1234 + r) for r in range(ROT)]
