@@ -1,0 +1,98 @@
+#!/usr/bin/env python
+"""Randomised parity sweep on a GPU box (not collected by pytest): random agent counts, densities, modes and solver
+settings, every step of the CUDA path held to the oracle with the bars of tests/_parity.py; every few cases the same
+configuration also goes through macm_rollout and is held to single steps.
+
+    python tests/fuzz_gpu.py [--seconds 180] [--seed 1]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "gym-macm_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from _parity import run_parity  # noqa: E402
+
+
+def rollout_case(rng, N, E, kw):
+    import torch
+    import gym_macm
+    K = int(rng.integers(5, 60))
+    seed = int(rng.integers(0, 1 << 30))
+    one, many = [gym_macm.BatchedFlock(E, n_agents=[N], device="cuda:0", seed=seed, **kw) for _ in range(2)]
+    if kw.get("action_mode") == "continuous":
+        acts = (torch.rand((K, E, N, 2), device="cuda:0") * 2.4 - 1.2).contiguous()
+    else:
+        acts = torch.zeros((K, E, N, 4), dtype=torch.uint8, device="cuda:0")
+        acts[..., :3] = torch.randint(0, 3, (K, E, N, 3), device="cuda:0", dtype=torch.uint8)
+    per = []
+    for k in range(K):
+        one.step(acts[k])
+        per.append((one.state["obs"].clone(), one.state["rewards"].clone(), one.state["nn_idx"].clone()))
+    out = many.rollout(acts)
+    torch.cuda.synchronize()
+    assert torch.equal(out["obs"], torch.stack([p[0] for p in per]))
+    assert torch.equal(out["rewards"], torch.stack([p[1] for p in per]))
+    assert torch.equal(out["nn_idx"], torch.stack([p[2] for p in per]))
+    for n in ("posvel", "angsleep", "fat", "contact_count", "env_state"):
+        assert torch.equal(one.state[n], many.state[n]), n
+    one.close()
+    many.close()
+    return K
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seconds", type=float, default=180.0)
+    ap.add_argument("--seed", type=int, default=1)
+    args = ap.parse_args()
+    rng = np.random.default_rng(args.seed)
+    t0, cases, agent_steps, worst_tc, skipped = time.time(), 0, 0, 0, 0
+    while time.time() - t0 < args.seconds:
+        N = int(rng.choice([2, 3, 4, 5, 6, 7, 8, 9, 12, 16, 17, 24, 31, 32, 33, 40, 45, 48, 63, 64]))
+        E = int(rng.choice([3, 16, 40]))
+        # side of the spawn square: from a pile (about one body area per agent) to the reference's 20 m
+        spread = float(np.sqrt(N) * rng.choice([0.9, 1.3, 2.0, 3.5]) if rng.random() < 0.7 else 20.0)
+        kw = dict(reward_mode=str(rng.choice(["binary", "linear"])), coord=str(rng.choice(["polar", "cartesian"])),
+                  action_mode=str(rng.choice(["discrete", "discrete", "continuous"])),
+                  damping_model=str(rng.choice(["taylor", "pade"])))
+        if rng.random() < 0.3:
+            kw.update(velocityIterations=int(rng.integers(1, 11)), positionIterations=int(rng.integers(0, 5)))
+        if rng.random() < 0.15:
+            kw.update(enableWarmStarting=False)
+        targets = None
+        if N >= 3 and rng.random() < 0.3:
+            T = int(rng.integers(2, min(N, 5) + 1))
+            targets = [int(i % T) for i in range(N)]
+        steps = int(rng.integers(30, 160))
+        policy = "random"
+        if kw["action_mode"] == "discrete" and kw["coord"] == "polar" and rng.random() < 0.25:
+            policy = str(rng.choice(["flock", "idle"]))
+        desc = dict(N=N, E=E, spread=round(spread, 2), steps=steps, policy=policy, targets=targets, **kw)
+        try:
+            st = run_parity(E, N, steps, targets=targets, seed=int(rng.integers(0, 1 << 30)), spread=spread, policy=policy,
+                            max_contacts=N * (N - 1) // 2, max_touching=240, **kw)
+            if cases % 4 == 0:
+                rollout_case(rng, N, E, {k: v for k, v in kw.items()})
+        except AssertionError as ex:
+            if "capacity overflow" in str(ex):   # more than 240 touching contacts: outside the staged solver's range
+                skipped += 1
+                continue
+            print("MISMATCH", json.dumps(desc), str(ex)[:300], flush=True)
+            sys.exit(1)
+        cases += 1
+        agent_steps += E * N * steps
+        worst_tc = max(worst_tc, st["max_touching"])
+    print(json.dumps({"cases": cases, "agent_steps_checked": agent_steps, "max_touching_seen": worst_tc, "skipped_overflow": skipped,
+                      "seconds": round(time.time() - t0, 1), "seed": args.seed}))
+
+
+if __name__ == "__main__":
+    main()
