@@ -19,6 +19,7 @@ for p in (ROOT, os.path.join(ROOT, "gym-macm_b200"), os.path.join(ROOT, "tests")
         sys.path.insert(0, p)
 
 from _parity import run_parity  # noqa: E402
+from test_gpu_tdm import run_tdm  # noqa: E402
 
 
 def rollout_case(rng, N, E, kw):
@@ -52,10 +53,31 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=180.0)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--tdm", type=float, default=0.2, help="share of team-deathmatch cases")
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
     t0, cases, agent_steps, worst_tc, skipped = time.time(), 0, 0, 0, 0
+    tdm_cases, deaths = 0, 0
     while time.time() - t0 < args.seconds:
+        if rng.random() < args.tdm:
+            n_teams = int(rng.integers(2, 5))
+            teams = [int(rng.integers(1, 64 // n_teams + 1)) for _ in range(n_teams)]
+            side = float(rng.choice([3.0, 6.0, 12.0, 30.0]))
+            desc = dict(kind="tdm", teams=teams, side=side)
+            try:
+                steps = int(rng.integers(100, 500))
+                E = int(rng.choice([4, 24]))
+                deaths += run_tdm(E, teams, steps, seed=int(rng.integers(0, 1 << 30)), width=side, height=side,
+                                  attack_p=float(rng.choice([0.2, 0.5, 0.9])), check_every=int(rng.choice([1, 7])))
+            except AssertionError as ex:
+                if "overflow" in str(ex):
+                    skipped += 1
+                    continue
+                print("MISMATCH", json.dumps(desc), str(ex)[:300], flush=True)
+                sys.exit(1)
+            tdm_cases += 1
+            agent_steps += E * sum(teams) * steps
+            continue
         N = int(rng.choice([2, 3, 4, 5, 6, 7, 8, 9, 12, 16, 17, 24, 31, 32, 33, 40, 45, 48, 63, 64]))
         E = int(rng.choice([3, 16, 40]))
         # side of the spawn square: from a pile (about one body area per agent) to the reference's 20 m
@@ -90,7 +112,7 @@ def main():
         cases += 1
         agent_steps += E * N * steps
         worst_tc = max(worst_tc, st["max_touching"])
-    print(json.dumps({"cases": cases, "agent_steps_checked": agent_steps, "max_touching_seen": worst_tc, "skipped_overflow": skipped,
+    print(json.dumps({"cases": cases, "tdm_cases": tdm_cases, "tdm_deaths_at_case_end": deaths, "agent_steps_checked": agent_steps, "max_touching_seen": worst_tc, "skipped_overflow": skipped,
                       "seconds": round(time.time() - t0, 1), "seed": args.seed}))
 
 
