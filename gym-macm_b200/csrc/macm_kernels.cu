@@ -983,6 +983,7 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
     int cd_atk[APL], cd_mov[APL], hits[APL];
     bool was_alive[APL];
     int team[APL];
+    float2 tg0[APL];   // the agent's target, on its way to shared memory
 #pragma unroll
     for (int s = 0; s < APL; ++s) {
         const int i = g.gl + s * G;
@@ -1005,7 +1006,9 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
             c[s] = make_float2(3.0e30f, 3.0e30f); v[s] = make_float2(0.0f, 0.0f);
             fatr[s] = make_float4(3.0e30f, 3.0e30f, 3.0e30f, 3.0e30f);
         }
-        if (!TDM) S.tgt()[i] = P.targets[(size_t)env * P.T + P.target_idx[valid[s] ? i : 0]];
+        // (one target: no index to fetch first -- one dependent global load less at the head of the step)
+        if (!TDM) tg0[s] = P.targets[(size_t)env * P.T + (P.T == 1 ? 0 : (int)P.target_idx[valid[s] ? i : 0])];
+        if (!TDM && ROLL) S.tgt()[i] = tg0[s];   // (a rollout stages it before its loop)
         // the flock actor steers by the target node of the last observation (bots.py:37-61)
         if (!TDM && R.policy() == MACM_BOT_FLOCK && valid[s]) {
             const float4 o4 = reinterpret_cast<const float4*>(P.obs)[gi];   // polar only (macm_rollout checks)
@@ -1044,10 +1047,6 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
             fatr[s] = reinterpret_cast<const float4*>(S.t_n())[i];
             slp[s] = reinterpret_cast<const float*>(reinterpret_cast<const float4*>(S.t_n()) + NC)[i];
         }
-        pos[i] = c[s];
-        fat[i] = fatr[s];
-        adj[i] = make_uint2(0u, 0u);
-        S.tmask()[i] = 0u;
         // discrete action word, fetched with the state (first step) / one step ahead into L2 (later steps)
         act_raw[s] = 0u;
         if (discrete && valid[s]) {
@@ -1124,6 +1123,18 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
             F[s].x = (float)(x * P.force);
             F[s].y = (float)(y * P.force);
         }
+    }
+    // The bodies reach shared memory only now: phase 1 needs nothing but the angle and the action word, so the
+    // rest of the state (positions, fat AABBs, contact list head, target) is still arriving from L2 while the
+    // float64 action decode runs -- the whole batch loads its state at the same moment and the L2 is the queue.
+#pragma unroll
+    for (int s = 0; s < APL; ++s) {
+        const int i = g.gl + s * G;
+        pos[i] = c[s];
+        fat[i] = fatr[s];
+        adj[i] = make_uint2(0u, 0u);
+        S.tmask()[i] = 0u;
+        if (!TDM && !ROLL) S.tgt()[i] = tg0[s];
     }
     g.sync();
 
