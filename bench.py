@@ -209,6 +209,9 @@ def main():
     ap.add_argument("--streams", type=int, default=1,
                     help="streams the independent batches of the rotation are spread over (a batch keeps its stream)")
     ap.add_argument("--gather", action="store_true", help="NCCL all-gather of obs+rewards every step")
+    ap.add_argument("--gather-peer", action="store_true",
+                    help="obs+rewards+done of every rank written into rank 0's buffers by the step kernel itself "
+                         "(gym_macm.dist.PeerGather: NVLink peer stores, no collective)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--e2e-steps", type=int, default=240)
     ap.add_argument("--e2e-depth", type=int, default=3, help="independent batches in flight on the host-buffer path")
@@ -275,9 +278,18 @@ def main():
     NS = max(1, min(args.streams, ROT))
     streams = [torch.cuda.Stream(device=dev) for _ in range(NS)] if NS > 1 else [None]
 
+    peer = None
+    if args.gather_peer and world > 1:
+        from gym_macm.dist import PeerGather
+        peer = [PeerGather(s_, world * E, learner=0, names=("obs", "rewards", "done")) for s_ in sims[:1]]
+        peer_out = peer[0].mine   # every batch of the rotation writes into the same two buffer sets on the learner
+
     def one_step(k):
         s = sims[k % ROT]
         st = streams[(k % ROT) % NS]
+        if peer is not None:
+            s.engine.rollout(acts[(k // ROT + 7 * (k % ROT)) % POOL], 1, None, 0, peer_out[k & 1], st)
+            return
         if args.policy == "flock":
             with torch.cuda.stream(st if st is not None else main_stream):
                 a = s.bot_actions("flock")
@@ -340,7 +352,7 @@ def main():
     #     long islands finishing alone) overlaps the next batch's body.  What a rollout worker with several
     #     env batches in flight gets.
     legs = {}
-    if NS == 1 and ROT >= 2 and gathered is None and args.policy == "random":
+    if NS == 1 and ROT >= 2 and gathered is None and peer is None and args.policy == "random":
         st2 = [torch.cuda.Stream(device=dev) for _ in range(2)]
         for rep_ in range(2):      # first pass = warm-up
             torch.cuda.synchronize()
@@ -362,7 +374,7 @@ def main():
                                 "note": "same steps, the rotation's batches alternating between two streams"}
     # (2) macm_rollout: R steps of a batch per launch, the envs' bodies held on chip between the steps; every
     #     step still writes its obs / nn_idx / rewards / collided / done (to per-step arrays).
-    if gathered is None and args.policy == "random" and args.rollout > 0:
+    if gathered is None and peer is None and args.policy == "random" and args.rollout > 0:
         R = min(args.rollout, POOL)
         outs = [sims[0].engine.rollout_buffers(R) for _ in range(2)]
         n_launch = max(ROT, (args.steps // R) // ROT * ROT)
@@ -463,7 +475,9 @@ def main():
                              % (ROT, ROT * E * N * 73 / 1e6),
                        "streams": NS, "numa_bound_cpus": len(numa_cpus) if numa_cpus else None,
                        "parallelism": "envs sharded, %d per GPU, no data-path collective%s" % (
-                           E, " + NCCL all-gather of obs/rewards" if gathered is not None else ""),
+                           E, " + NCCL all-gather of obs/rewards" if gathered is not None else (
+                               " + obs/rewards/done stored into rank 0's buffers by the step kernel (NVLink peer stores)"
+                               if peer is not None else "")),
                        "launch": {"lanes_per_env": info.lanes_per_env, "agents_per_lane": info.agents_per_lane,
                                   "threads_per_block": info.threads_per_block, "blocks": info.blocks,
                                   "smem_per_block": info.smem_bytes_per_block, "blocks_per_sm": info.blocks_per_sm},

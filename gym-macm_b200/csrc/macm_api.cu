@@ -443,6 +443,57 @@ extern "C" int macm_host_alloc(void** out, uint64_t bytes)
 
 extern "C" int macm_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? MACM_OK : MACM_E_CUDA; }
 
+extern "C" int macm_enable_peer_access(int device, int peer_device)
+{
+    if (device == peer_device) return MACM_OK;
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, device, peer_device) != cudaSuccess || !can) return MACM_E_UNSUPPORTED;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cudaSetDevice(device) != cudaSuccess) return MACM_E_CUDA;
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+    cudaSetDevice(cur);
+    return e == cudaSuccess ? MACM_OK : MACM_E_CUDA;
+}
+
+extern "C" int macm_device_alloc(int device, uint64_t bytes, void** out, void* ipc_handle_out)
+{
+    if (!out || bytes == 0) return MACM_E_INVALID;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cudaSetDevice(device) != cudaSuccess) return MACM_E_CUDA;
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaSuccess) e = cudaMemset(*out, 0, bytes);
+    if (e == cudaSuccess && ipc_handle_out) {
+        cudaIpcMemHandle_t h;
+        e = cudaIpcGetMemHandle(&h, *out);
+        if (e == cudaSuccess) memcpy(ipc_handle_out, &h, sizeof(h));
+    }
+    if (e != cudaSuccess) { fprintf(stderr, "macm_device_alloc: %s\n", cudaGetErrorString(e)); cudaGetLastError(); }
+    cudaSetDevice(cur);
+    return e == cudaSuccess ? MACM_OK : MACM_E_CUDA;
+}
+
+extern "C" int macm_device_free(void* p) { return cudaFree(p) == cudaSuccess ? MACM_OK : MACM_E_CUDA; }
+
+extern "C" int macm_ipc_open(const void* handle, int device, void** out)
+{
+    if (!handle || !out) return MACM_E_INVALID;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cudaSetDevice(device) != cudaSuccess) return MACM_E_CUDA;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    // opened on the device whose kernels will use the mapping: peer access to the exporting GPU is set up with it
+    cudaError_t e = cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { fprintf(stderr, "macm_ipc_open: %s\n", cudaGetErrorString(e)); cudaGetLastError(); }
+    cudaSetDevice(cur);
+    return e == cudaSuccess ? MACM_OK : MACM_E_CUDA;
+}
+
+extern "C" int macm_ipc_close(void* base) { return cudaIpcCloseMemHandle(base) == cudaSuccess ? MACM_OK : MACM_E_CUDA; }
+
 extern "C" int macm_set_trace(macm_sim* sim, void* trace)
 {
     if (!sim) return MACM_E_INVALID;

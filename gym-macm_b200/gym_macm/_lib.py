@@ -63,7 +63,8 @@ EXPORTS = ("macm_abi_version", "macm_strerror", "macm_last_cuda_error", "macm_pa
            "macm_destroy", "macm_get_buffer_sizes", "macm_get_launch_info", "macm_bind", "macm_reset",
            "macm_sample_reset", "macm_step", "macm_rollout", "macm_observe", "macm_bot_actions", "macm_step_host", "macm_step_host_async", "macm_host_sync",
            "macm_host_alloc",
-           "macm_host_free", "macm_launch_count", "macm_set_trace")
+           "macm_host_free", "macm_launch_count", "macm_set_trace", "macm_enable_peer_access", "macm_ipc_open",
+           "macm_ipc_close", "macm_device_alloc", "macm_device_free")
 
 
 class MacmError(RuntimeError):
@@ -107,6 +108,11 @@ def lib():
         L.macm_launch_count.restype = C.c_int64
         L.macm_launch_count.argtypes = [vp]
         L.macm_set_trace.argtypes = [vp, vp]
+        L.macm_enable_peer_access.argtypes = [C.c_int, C.c_int]
+        L.macm_ipc_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+        L.macm_ipc_close.argtypes = [vp]
+        L.macm_device_alloc.argtypes = [C.c_int, u64, C.POINTER(vp), C.c_char_p]
+        L.macm_device_free.argtypes = [vp]
         if L.macm_abi_version() != 2:
             raise MacmError("libmacm.so ABI version mismatch")
         _lib = L

@@ -43,6 +43,74 @@ def bind_to_gpu_numa(local_rank):
         return None
 
 
+class _SharedAlloc(object):
+    """A cudaMalloc'ed block owned through the C ABI, visible to torch through __cuda_array_interface__."""
+
+    def __init__(self, nbytes, device):
+        import ctypes as C
+        from gym_macm import _lib
+        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        _lib.check(_lib.lib().macm_device_alloc(int(device), int(nbytes), C.byref(ptr), handle))
+        self.ptr, self.nbytes, self.handle = ptr.value, int(nbytes), handle.raw
+        self.__cuda_array_interface__ = {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 2}
+
+    def __del__(self):
+        try:
+            from gym_macm import _lib
+            _lib.lib().macm_device_free(self.ptr)
+        except Exception:
+            pass
+
+
+def alloc_shared(shape, dtype, device):
+    """(tensor, meta): a zeroed device tensor in an allocation of its own, and the picklable description the other
+    ranks of the box feed to open_peer_tensor() (send it with broadcast_object_list)."""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    mem = _SharedAlloc(max(1, n) * torch.empty((), dtype=dtype).element_size(), device)
+    t = torch.as_tensor(mem, device=torch.device("cuda", int(device))).view(dtype).view(tuple(shape))
+    t._macm_owner = mem   # the allocation lives as long as the tensor
+    return t, {"handle": mem.handle, "alloc_offset": 0, "offset": 0, "dtype": dtype, "shape": tuple(shape)}
+
+
+class PeerBuffer(object):
+    """A contiguous array in ANOTHER process's device memory, mapped for this rank's kernels (raw address + shape):
+    enough for the C ABI, which only wants pointers.  Slicing the leading axis gives a view."""
+
+    def __init__(self, ptr, shape, dtype, base=None):
+        self.ptr, self.shape, self.dtype, self.base = int(ptr), tuple(shape), dtype, base
+
+    def data_ptr(self):
+        return self.ptr
+
+    def __getitem__(self, sl):
+        lo, hi, step = sl.indices(self.shape[0])
+        assert step == 1
+        row = torch.empty((), dtype=self.dtype).element_size()
+        for d in self.shape[1:]:
+            row *= d
+        return PeerBuffer(self.ptr + lo * row, (hi - lo,) + self.shape[1:], self.dtype, self.base)
+
+
+def open_peer_tensor(meta, device=None):
+    """Map another rank's device tensor for kernels of `device` (default: the current one): cudaIpcOpenMemHandle on
+    that device with lazy peer access, i.e. plain loads/stores over NVLink."""
+    import ctypes as C
+    from gym_macm import _lib
+    device = torch.cuda.current_device() if device is None else int(device)
+    key = (device, meta["handle"])
+    if key not in _OPENED:     # an allocation is mapped once per process; tensors that share it share the mapping
+        base = C.c_void_p()
+        _lib.check(_lib.lib().macm_ipc_open(meta["handle"], device, C.byref(base)))
+        _OPENED[key] = base.value
+    base = _OPENED[key]
+    return PeerBuffer(base + meta["alloc_offset"] + meta["offset"], meta["shape"], meta["dtype"], base)
+
+
+_OPENED = {}
+
+
 def shard_range(n_total, rank, world):
     """Contiguous env range [start, start+count) of `rank`; the first n_total % world ranks get one more."""
     base, rem = divmod(int(n_total), int(world))
@@ -89,6 +157,57 @@ def scatter_actions(actions_full, n_total, src=0, group=None, device=None, like=
     dist.broadcast(buf, src=src, group=group)
     start, count = shard_range(n_total, rank, world)
     return buf[start:start + count]
+
+
+class PeerGather(object):
+    """The learner-side gather fused into the step: every rank's kernel stores its observations, rewards and done
+    flags straight into the LEARNER rank's buffers (NVLink peer stores through CUDA IPC mappings), next to its own
+    bound buffers.  No collective, no staging copy: the transfer rides on the step kernel, agent by agent.
+
+    The step runs through macm_rollout with one step per launch, whose per-step output pointers may point
+    anywhere -- here at this shard's rows of the learner's [n_total, ...] arrays.  `n_buffers` sets of arrays
+    rotate (the learner reads set k while the shards fill set k+1).  Every rank of the group must call the
+    constructor; `fence()` makes a filled set visible to the learner (stream sync on every rank + barrier)."""
+
+    NAMES = ("obs", "nn_idx", "rewards", "collided", "done")
+
+    def __init__(self, env, n_total, learner=0, names=("obs", "rewards", "done"), n_buffers=2, group=None):
+        self.env, self.group, self.learner = env, group, learner
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.start, self.count = shard_range(n_total, self.rank, self.world)
+        eng = env.engine
+        assert self.count == eng.E, "the env batch of this rank must be its shard of n_total"
+        self.names = tuple(n for n in names if n in eng.t)
+        self.full, self.mine = [], []
+        for b in range(n_buffers):
+            if self.rank == learner:
+                made = {n: alloc_shared((n_total,) + tuple(eng.t[n].shape[1:]), eng.t[n].dtype, eng.device.index)
+                        for n in self.names}
+                full = {n: v[0] for n, v in made.items()}
+                meta = [{n: v[1] for n, v in made.items()}]
+            else:
+                full, meta = None, [None]
+            dist.broadcast_object_list(meta, src=learner, group=group)
+            if self.rank != learner:
+                full = {n: open_peer_tensor(m, eng.device.index) for n, m in meta[0].items()}
+            self.full.append(full)
+            self.mine.append({n: t[self.start:self.start + self.count] for n, t in full.items()})
+        self.k = 0
+
+    def step(self, actions, stream=None):
+        """One step of this rank's shard; its outputs land in buffer set `self.k % n_buffers` on the learner."""
+        out = self.mine[self.k % len(self.mine)]
+        self.env.engine.rollout(actions, 1, None, 0, out, stream)
+        self.k += 1
+        return out
+
+    def fence(self):
+        torch.cuda.current_stream(self.env.engine.device).synchronize()
+        dist.barrier(group=self.group)
+
+    def gathered(self, back=1):
+        """On the learner: the buffer set filled `back` steps ago (call fence() first)."""
+        return self.full[(self.k - back) % len(self.full)]
 
 
 class ShardedFlock(object):

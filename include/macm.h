@@ -243,6 +243,19 @@ int macm_host_sync(macm_sim* sim);
 int macm_host_alloc(void** out, uint64_t bytes);
 int macm_host_free(void* p);
 
+/* Lets kernels running on `device` load and store memory that lives on `peer_device` (NVLink / PCIe peer access;
+ * idempotent).  Needed once per process before a macm_rollout_out pointer may name another GPU's buffer -- the
+ * learner-side gather of BASELINE config 5 done by the step kernel itself (gym_macm.dist.PeerGather). */
+int macm_enable_peer_access(int device, int peer_device);
+/* A zeroed device allocation of its own (cudaMalloc, not a slice of the host framework's pool) together with the
+ * 64 bytes of its cudaIpcMemHandle_t (ipc_handle_out may be NULL): what the learner rank exports to the others. */
+int macm_device_alloc(int device, uint64_t bytes, void** out, void* ipc_handle_out);
+int macm_device_free(void* p);
+/* Maps a device allocation exported by another process of the box (`handle` = the 64 bytes of its
+ * cudaIpcMemHandle_t) for kernels running on `device`; *out receives the base address of the allocation. */
+int macm_ipc_open(const void* handle, int device, void** out);
+int macm_ipc_close(void* base);
+
 /* Number of kernels this handle has launched so far. */
 int64_t macm_launch_count(const macm_sim* sim);
 
