@@ -1030,13 +1030,6 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
     // cache on their own, which saturates (gcc requests 83 % of peak, "no instruction" the top stall) -- in step
     // they share every fetched line.
     if (R.sync() > 0 && ks > 0 && (ks % R.sync()) == 0) __syncthreads();
-    if (R.sync() < 0 && ks > 0 && G == 32 && (ks % (-R.sync())) == 0) {
-        // the warps of one sub-partition (warp id mod 4) start the step together: they share that sub-partition's L0
-        const int warps_live = min((int)blockDim.x / 32, P.E - (int)blockIdx.x * ((int)blockDim.x / 32));
-        const int q = (threadIdx.x >> 5) & 3;
-        const int members = (warps_live - q + 3) / 4;
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(members * 32) : "memory");
-    }
     g.sync();   // the previous step's observation pass has finished reading the staging arrays
 #pragma unroll
     for (int s = 0; s < APL; ++s) {

@@ -56,7 +56,7 @@ struct SimConst {
 // null); the sim's bound output buffers receive the last step's values, exactly as after K calls of macm_step.
 struct Rollout {
     int K;              // steps in this launch (macm_step: 1)
-    int sync;           // experiment: block barrier every `sync` steps (0 = never)
+    int sync;           // the block's warps start every `sync`-th step together (0 = never; 1 with one block per SM)
     int policy;         // MACM_BOT_* when `actions` is null (the actions=None mode of mvmnt.py:86-92), else -1
     unsigned long long seed;
     float* obs; int* nn_idx; float* rewards; uint8_t* collided; uint8_t* done;
