@@ -879,24 +879,28 @@ __device__ __noinline__ uint32_t bot_action(const SimConst& P, const Rollout& R,
 // ------------------------------------------------------------------------------------------
 // the step kernel
 // ------------------------------------------------------------------------------------------
-// ROLL = false: one step per launch (macm_step); every rollout argument folds away at compile time.
-// ROLL = true: R.K steps per launch (macm_rollout), the env's bodies staying in registers / shared memory.
-template <int G, int APL, int KIND, bool ROLL>
+// MODE 0: one step per launch (macm_step); every rollout argument folds away at compile time.
+// MODE 1: R.K steps per launch (macm_rollout), the env's bodies staying in registers / shared memory.
+// MODE 2: one step per launch whose outputs ALSO go to the caller's per-step arrays (macm_rollout with n_steps = 1
+//         and given actions -- the shape gym_macm.dist.PeerGather uses to store into the learner's memory): the
+//         single-step code plus the second stores, none of the loop-carried state of MODE 1.
+template <int G, int APL, int KIND, int MODE>
 __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const __grid_constant__ SimConst P,
                                                         const void* __restrict__ actions,
                                                         const __grid_constant__ Rollout R_)
 {
     // the single-step kernel sees compile-time constants instead of the rollout arguments
+    constexpr bool ROLL = MODE == 1;   // the multi-step loop with its parked state
     struct RollView {
         const Rollout& r;
-        __device__ int K() const { return ROLL ? r.K : 1; }
-        __device__ int policy() const { return ROLL ? r.policy : -1; }
-        __device__ int sync() const { return ROLL ? r.sync : 0; }
-        __device__ float* obs() const { return ROLL ? r.obs : nullptr; }
-        __device__ int* nn_idx() const { return ROLL ? r.nn_idx : nullptr; }
-        __device__ float* rewards() const { return ROLL ? r.rewards : nullptr; }
-        __device__ uint8_t* collided() const { return ROLL ? r.collided : nullptr; }
-        __device__ uint8_t* done() const { return ROLL ? r.done : nullptr; }
+        __device__ int K() const { return MODE == 1 ? r.K : 1; }
+        __device__ int policy() const { return MODE == 1 ? r.policy : -1; }
+        __device__ int sync() const { return MODE == 1 ? r.sync : 0; }
+        __device__ float* obs() const { return MODE ? r.obs : nullptr; }
+        __device__ int* nn_idx() const { return MODE ? r.nn_idx : nullptr; }
+        __device__ float* rewards() const { return MODE ? r.rewards : nullptr; }
+        __device__ uint8_t* collided() const { return MODE ? r.collided : nullptr; }
+        __device__ uint8_t* done() const { return MODE ? r.done : nullptr; }
     };
     const RollView R{R_};
     constexpr int NC = G * APL;
@@ -1768,23 +1772,28 @@ cudaError_t launch_one(const SimConst& P, const LaunchCfg& cfg, const void* acti
     at[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = at;
     lc.numAttrs = 1;
-    if (R.K == 1 && R.policy < 0 && !R.obs && !R.nn_idx && !R.rewards && !R.collided && !R.done)
-        return cudaLaunchKernelEx(&lc, macm_step_kernel<G, APL, KIND, false>, P, actions, R);
-    return cudaLaunchKernelEx(&lc, macm_step_kernel<G, APL, KIND, true>, P, actions, R);
+    if (R.K == 1 && R.policy < 0 && actions) {
+        if (!R.obs && !R.nn_idx && !R.rewards && !R.collided && !R.done)
+            return cudaLaunchKernelEx(&lc, macm_step_kernel<G, APL, KIND, 0>, P, actions, R);
+        return cudaLaunchKernelEx(&lc, macm_step_kernel<G, APL, KIND, 2>, P, actions, R);
+    }
+    return cudaLaunchKernelEx(&lc, macm_step_kernel<G, APL, KIND, 1>, P, actions, R);
 }
 
 template <int G, int APL, int KIND>
 cudaError_t prepare_one(const LaunchCfg& cfg, int* blocks_per_sm)
 {
-    cudaError_t e = cudaFuncSetAttribute(macm_step_kernel<G, APL, KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(macm_step_kernel<G, APL, KIND, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          cfg.smem_bytes);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(macm_step_kernel<G, APL, KIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.smem_bytes);
+    e = cudaFuncSetAttribute(macm_step_kernel<G, APL, KIND, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.smem_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(macm_step_kernel<G, APL, KIND, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.smem_bytes);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(macm_observe_kernel<G, APL, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              cfg.obs_smem_bytes);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, macm_step_kernel<G, APL, KIND, false>, cfg.threads,
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, macm_step_kernel<G, APL, KIND, 0>, cfg.threads,
                                                          cfg.smem_bytes);
 }
 
