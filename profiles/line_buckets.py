@@ -13,8 +13,8 @@ from collections import defaultdict
 src_csv, dis_txt = sys.argv[1:3]
 cu = sys.argv[3] if len(sys.argv) > 3 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                                                         "gym-macm_b200", "csrc", "macm_kernels.cu")
-kname = sys.argv[4] if len(sys.argv) > 4 else "macm_step_kernelILi32ELi2ELi0ELb0"
-dname = sys.argv[5] if len(sys.argv) > 5 else "macm_step_kernel<(int)32, (int)2, (int)0, (bool)0>"
+kname = sys.argv[4] if len(sys.argv) > 4 else "macm_step_kernelILi32ELi2ELi0ELi0"
+dname = sys.argv[5] if len(sys.argv) > 5 else "macm_step_kernel<(int)32, (int)2, (int)0, (int)0>"
 E = int(sys.argv[6]) if len(sys.argv) > 6 else 4096
 
 marks = []   # (first line, name)
