@@ -60,3 +60,18 @@ def test_gather_and_scatter_world2_gloo(total):
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_peer_buffer_views_and_numa_binding_without_a_gpu():
+    from gym_macm.dist import PeerBuffer, bind_to_gpu_numa
+    # a mapped array of another process: slicing the env axis moves the address by whole rows
+    b = PeerBuffer(4096, (10, 3, 4), torch.float32)
+    v = b[2:5]
+    assert v.data_ptr() == 4096 + 2 * 3 * 4 * 4 and v.shape == (3, 3, 4) and v.dtype == torch.float32
+    assert b[7:].shape == (3, 3, 4) and b[7:].data_ptr() == 4096 + 7 * 48
+    u = PeerBuffer(64, (5,), torch.uint8)[1:2]
+    assert u.data_ptr() == 65 and u.shape == (1,)
+    # no NVML device here: the binding helper declines quietly and leaves the affinity alone
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa(0) is None
+    assert os.sched_getaffinity(0) == before
