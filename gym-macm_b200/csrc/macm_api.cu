@@ -25,6 +25,28 @@ struct macm_sim {
     void* d_actions;
     size_t d_actions_bytes;
     double2* d_sincos;
+    int* d_scratch;            // two counters (macm_overflow_count)
+    uint64_t auto_seed;        // seed of the resets appended under MACM_FLAG_AUTO_RESET
+    // Ordering between the caller's streams and the handle's own host-path stream: the last stream an entry point
+    // enqueued device work on, whether that work is still unordered against hstream, and the reverse.  Events are
+    // recorded lazily, at the moment the other side is used -- nothing is inserted between two step launches
+    // (an event between them would end their programmatic overlap).
+    cudaStream_t last_stream;
+    int dev_dirty, host_dirty;
+    cudaEvent_t ev_dev, ev_host;
+};
+
+// Every entry point that launches or allocates runs with the handle's device current and puts the caller's device
+// back on return (a handle may be driven from a thread whose current device is another GPU).
+struct DevGuard {
+    int prev;
+    bool ok;
+    explicit DevGuard(int device) : prev(-1), ok(true)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) ok = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
 static int fail_cuda(macm_sim* s, cudaError_t e, const char* where)
@@ -37,6 +59,53 @@ static int fail_cuda(macm_sim* s, cudaError_t e, const char* where)
         cudaError_t e_ = (call);                                   \
         if (e_ != cudaSuccess) return fail_cuda(sim, e_, #call);   \
     } while (0)
+
+#define GUARD()                                                                  \
+    DevGuard guard_(sim->device);                                                \
+    if (!guard_.ok) return fail_cuda(sim, cudaGetLastError(), "cudaSetDevice")
+
+// device work was enqueued on `s` by a caller-stream entry point
+static void note_device_work(macm_sim* sim, cudaStream_t s) { sim->last_stream = s; sim->dev_dirty = 1; }
+
+// `s` (a caller's stream) is about to touch the bound buffers: order it after whatever the host path enqueued
+static int order_after_host(macm_sim* sim, cudaStream_t s)
+{
+    if (sim->host_dirty && sim->hstream) {
+        CU(cudaEventRecord(sim->ev_host, sim->hstream));
+        CU(cudaStreamWaitEvent(s, sim->ev_host, 0));
+        sim->host_dirty = 0;
+    }
+    return MACM_OK;
+}
+
+// the host path is about to touch the bound buffers: order hstream after the caller-stream work seen so far
+static int order_after_device(macm_sim* sim)
+{
+    if (sim->dev_dirty) {
+        CU(cudaEventRecord(sim->ev_dev, sim->last_stream));
+        CU(cudaStreamWaitEvent(sim->hstream, sim->ev_dev, 0));
+        sim->dev_dirty = 0;
+    }
+    return MACM_OK;
+}
+
+static SampleConst sample_const(const macm_sim* sim, uint64_t seed)
+{
+    const macm_params& p = sim->params;
+    SampleConst sc;
+    sc.seed = seed; sc.spread = p.start_spread; sc.sx = p.start_x; sc.sy = p.start_y;
+    sc.tmin = p.target_mindist; sc.tmax = p.target_maxdist; sc.width = p.world_width; sc.height = p.world_height;
+    return sc;
+}
+
+// MACM_FLAG_AUTO_RESET: the launch that follows every step / rollout launch
+static int auto_reset(macm_sim* sim, cudaStream_t s)
+{
+    if (!(sim->params.flags & MACM_FLAG_AUTO_RESET)) return MACM_OK;
+    CU(macm_launch_reset_masked(sim->K, sim->cfg, nullptr, sample_const(sim, sim->auto_seed), s));
+    sim->launches += 1;
+    return MACM_OK;
+}
 
 extern "C" int macm_abi_version(void) { return MACM_ABI_VERSION; }
 
@@ -214,8 +283,10 @@ extern "C" int macm_create(macm_sim** out, const macm_params* p, int device)
         delete sim;
         return MACM_E_CUDA;
     }
+    // the handle is returned even when a CUDA call below fails, so that macm_last_cuda_error can say why;
+    // the caller destroys it (macm_destroy frees whatever was allocated)
     *out = sim;
-    CU(cudaSetDevice(device));
+    GUARD();
     CU(cudaDeviceGetAttribute(&sim->sm_count, cudaDevAttrMultiProcessorCount, device));
     e = macm_launch_cfg(sim->K, sim->sm_count, &sim->cfg);
     if (e != cudaSuccess) { *out = nullptr; delete sim; return MACM_E_INVALID; }
@@ -229,16 +300,24 @@ extern "C" int macm_create(macm_sim** out, const macm_params* p, int device)
         CU(cudaMemcpy(sim->d_sincos, tab, sizeof(tab), cudaMemcpyHostToDevice));
         sim->K.sincos_tab = sim->d_sincos;
     }
+    CU(cudaMalloc((void**)&sim->d_scratch, 2 * sizeof(int)));
+    CU(cudaEventCreateWithFlags(&sim->ev_dev, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&sim->ev_host, cudaEventDisableTiming));
     return MACM_OK;
 }
 
 extern "C" int macm_destroy(macm_sim* sim)
 {
     if (!sim) return MACM_E_INVALID;
-    cudaSetDevice(sim->device);
-    if (sim->d_actions) cudaFree(sim->d_actions);
-    if (sim->d_sincos) cudaFree(sim->d_sincos);
-    if (sim->hstream) cudaStreamDestroy(sim->hstream);
+    {
+        DevGuard guard_(sim->device);
+        if (sim->d_actions) cudaFree(sim->d_actions);
+        if (sim->d_sincos) cudaFree(sim->d_sincos);
+        if (sim->d_scratch) cudaFree(sim->d_scratch);
+        if (sim->ev_dev) cudaEventDestroy(sim->ev_dev);
+        if (sim->ev_host) cudaEventDestroy(sim->ev_host);
+        if (sim->hstream) cudaStreamDestroy(sim->hstream);
+    }
     delete sim;
     return MACM_OK;
 }
@@ -303,10 +382,12 @@ extern "C" int macm_reset(macm_sim* sim, void* stream)
 {
     if (!sim) return MACM_E_INVALID;
     if (!sim->bound) return MACM_E_UNBOUND;
-    CU(cudaSetDevice(sim->device));
+    GUARD();
+    if (int rc = order_after_host(sim, (cudaStream_t)stream)) return rc;
     CU(macm_launch_reset(sim->K, (cudaStream_t)stream));
     CU(macm_launch_observe(sim->K, sim->cfg, (cudaStream_t)stream));
     sim->launches += 2;
+    note_device_work(sim, (cudaStream_t)stream);
     return MACM_OK;
 }
 
@@ -314,12 +395,59 @@ extern "C" int macm_sample_reset(macm_sim* sim, uint64_t seed, void* stream)
 {
     if (!sim) return MACM_E_INVALID;
     if (!sim->bound) return MACM_E_UNBOUND;
-    const macm_params& p = sim->params;
-    CU(cudaSetDevice(sim->device));
-    CU(macm_launch_sample(sim->K, seed, p.start_spread, p.start_x, p.start_y, p.target_mindist, p.target_maxdist,
-                          p.world_width, p.world_height, (cudaStream_t)stream));
+    GUARD();
+    if (int rc = order_after_host(sim, (cudaStream_t)stream)) return rc;
+    CU(macm_launch_sample(sim->K, sample_const(sim, seed), (cudaStream_t)stream));
     sim->launches += 1;
     return macm_reset(sim, stream);
+}
+
+extern "C" int macm_reset_masked(macm_sim* sim, const uint8_t* mask, uint64_t seed, void* stream)
+{
+    if (!sim) return MACM_E_INVALID;
+    if (!sim->bound) return MACM_E_UNBOUND;
+    GUARD();
+    if (int rc = order_after_host(sim, (cudaStream_t)stream)) return rc;
+    CU(macm_launch_reset_masked(sim->K, sim->cfg, mask, sample_const(sim, seed), (cudaStream_t)stream));
+    sim->launches += 1;
+    note_device_work(sim, (cudaStream_t)stream);
+    return MACM_OK;
+}
+
+extern "C" int macm_set_auto_reset_seed(macm_sim* sim, uint64_t seed)
+{
+    if (!sim) return MACM_E_INVALID;
+    sim->auto_seed = seed;
+    return MACM_OK;
+}
+
+extern "C" int macm_overflow_count(macm_sim* sim, int32_t* contact_envs, int32_t* touching_envs, void* stream)
+{
+    if (!sim) return MACM_E_INVALID;
+    if (!sim->bound) return MACM_E_UNBOUND;
+    GUARD();
+    if (int rc = order_after_host(sim, (cudaStream_t)stream)) return rc;
+    CU(macm_launch_overflow_count(sim->K, sim->d_scratch, (cudaStream_t)stream));
+    sim->launches += 1;
+    int h[2] = {0, 0};
+    CU(cudaMemcpyAsync(h, sim->d_scratch, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    if (contact_envs) *contact_envs = h[0];
+    if (touching_envs) *touching_envs = h[1];
+    return MACM_OK;
+}
+
+extern "C" int macm_pack_actions(macm_sim* sim, const void* src, int32_t elem_bytes, int32_t width, void* actions_out,
+                                 void* stream)
+{
+    if (!sim || !src || !actions_out) return MACM_E_INVALID;
+    if ((elem_bytes != 1 && elem_bytes != 2 && elem_bytes != 4 && elem_bytes != 8) || (width != 3 && width != 4))
+        return MACM_E_INVALID;
+    if (!aligned(actions_out, 4)) return MACM_E_ALIGN;
+    GUARD();
+    CU(macm_launch_pack_actions(src, elem_bytes, width, (uint64_t)sim->K.E * sim->K.N, actions_out, (cudaStream_t)stream));
+    sim->launches += 1;
+    return MACM_OK;
 }
 
 extern "C" int macm_step(macm_sim* sim, const void* actions, void* stream)
@@ -327,12 +455,15 @@ extern "C" int macm_step(macm_sim* sim, const void* actions, void* stream)
     if (!sim || !actions) return MACM_E_INVALID;
     if (!sim->bound) return MACM_E_UNBOUND;
     if (!aligned(actions, sim->params.action_mode == MACM_ACTION_DISCRETE ? 4 : 8)) return MACM_E_ALIGN;
+    GUARD();
+    if (int rc = order_after_host(sim, (cudaStream_t)stream)) return rc;
     Rollout R = {};
     R.K = 1;
     R.policy = -1;
     CU(macm_launch_step(sim->K, sim->cfg, actions, R, (cudaStream_t)stream));
     sim->launches += 1;
-    return MACM_OK;
+    note_device_work(sim, (cudaStream_t)stream);
+    return auto_reset(sim, (cudaStream_t)stream);
 }
 
 extern "C" int macm_rollout(macm_sim* sim, const void* actions, int32_t n_steps, int32_t policy, uint64_t seed,
@@ -351,10 +482,11 @@ extern "C" int macm_rollout(macm_sim* sim, const void* actions, int32_t n_steps,
         if (!aligned(actions, discrete ? 4 : 8)) return MACM_E_ALIGN;
     } else {
         // actions=None: every agent's actor decides from its own observation (mvmnt.py:86-92)
-        if (policy < MACM_BOT_IDLE || policy > MACM_BOT_RANDOM) return policy == MACM_BOT_COMBAT ? MACM_E_UNSUPPORTED : MACM_E_INVALID;
+        if (policy < MACM_BOT_IDLE || policy > MACM_BOT_CIRCLE) return MACM_E_INVALID;
         if (!discrete) return MACM_E_UNSUPPORTED;
         if (policy == MACM_BOT_FLOCK && (sim->K.kind != MACM_ENV_FLOCK || sim->params.coord != MACM_COORD_POLAR))
             return MACM_E_UNSUPPORTED;
+        if (policy == MACM_BOT_COMBAT && sim->K.kind != MACM_ENV_TDM) return MACM_E_UNSUPPORTED;
         R.policy = policy;
     }
     if (out) {
@@ -363,17 +495,23 @@ extern "C" int macm_rollout(macm_sim* sim, const void* actions, int32_t n_steps,
             return MACM_E_ALIGN;
         R.obs = out->obs; R.nn_idx = out->nn_idx; R.rewards = out->rewards; R.collided = out->collided; R.done = out->done;
     }
+    GUARD();
+    if (int rc = order_after_host(sim, (cudaStream_t)stream)) return rc;
     CU(macm_launch_step(sim->K, sim->cfg, actions, R, (cudaStream_t)stream));
     sim->launches += 1;
-    return MACM_OK;
+    note_device_work(sim, (cudaStream_t)stream);
+    return auto_reset(sim, (cudaStream_t)stream);
 }
 
 extern "C" int macm_observe(macm_sim* sim, void* stream)
 {
     if (!sim) return MACM_E_INVALID;
     if (!sim->bound) return MACM_E_UNBOUND;
+    GUARD();
+    if (int rc = order_after_host(sim, (cudaStream_t)stream)) return rc;
     CU(macm_launch_observe(sim->K, sim->cfg, (cudaStream_t)stream));
     sim->launches += 1;
+    note_device_work(sim, (cudaStream_t)stream);
     return MACM_OK;
 }
 
@@ -381,9 +519,12 @@ extern "C" int macm_bot_actions(macm_sim* sim, int policy, uint64_t seed, void* 
 {
     if (!sim || !actions_out) return MACM_E_INVALID;
     if (!sim->bound) return MACM_E_UNBOUND;
-    if (policy < MACM_BOT_IDLE || policy > MACM_BOT_COMBAT) return MACM_E_INVALID;
+    if (policy < MACM_BOT_IDLE || policy > MACM_BOT_CIRCLE) return MACM_E_INVALID;
     if (sim->params.action_mode != MACM_ACTION_DISCRETE) return MACM_E_UNSUPPORTED;
-    if (policy == MACM_BOT_COMBAT && sim->K.kind != MACM_ENV_TDM) return MACM_E_INVALID;
+    if (policy == MACM_BOT_COMBAT && sim->K.kind != MACM_ENV_TDM) return MACM_E_UNSUPPORTED;
+    if (policy == MACM_BOT_FLOCK && sim->K.kind != MACM_ENV_FLOCK) return MACM_E_UNSUPPORTED;
+    GUARD();
+    if (int rc = order_after_host(sim, (cudaStream_t)stream)) return rc;
     CU(macm_launch_bot(sim->K, policy, seed, actions_out, (cudaStream_t)stream));
     sim->launches += 1;
     return MACM_OK;
@@ -394,7 +535,7 @@ extern "C" int macm_step_host_async(macm_sim* sim, const void* actions, float* o
 {
     if (!sim || !actions) return MACM_E_INVALID;
     if (!sim->bound) return MACM_E_UNBOUND;
-    CU(cudaSetDevice(sim->device));
+    GUARD();
     macm_buffer_sizes z;
     macm_get_buffer_sizes(sim, &z);
     const size_t abytes = (size_t)sim->K.E * sim->K.N * z.action_bytes;
@@ -407,17 +548,41 @@ extern "C" int macm_step_host_async(macm_sim* sim, const void* actions, float* o
         sim->d_actions_bytes = abytes;
     }
     cudaStream_t s = sim->hstream;
+    // resets, steps, state loads enqueued on the caller's streams so far come first
+    if (int rc = order_after_device(sim)) return rc;
     CU(cudaMemcpyAsync(sim->d_actions, actions, abytes, cudaMemcpyHostToDevice, s));
     Rollout R = {};
     R.K = 1;
     R.policy = -1;
     CU(macm_launch_step(sim->K, sim->cfg, sim->d_actions, R, s));
     sim->launches += 1;
-    if (obs) CU(cudaMemcpyAsync(obs, sim->K.obs, z.obs, cudaMemcpyDeviceToHost, s));
-    if (rewards) CU(cudaMemcpyAsync(rewards, sim->K.rewards, z.rewards, cudaMemcpyDeviceToHost, s));
-    if (nn_idx && sim->K.nn_idx) CU(cudaMemcpyAsync(nn_idx, sim->K.nn_idx, z.nn_idx, cudaMemcpyDeviceToHost, s));
-    if (collided) CU(cudaMemcpyAsync(collided, sim->K.collided, z.collided, cudaMemcpyDeviceToHost, s));
-    if (done) CU(cudaMemcpyAsync(done, sim->K.done, z.done, cudaMemcpyDeviceToHost, s));
+    if (int rc = auto_reset(sim, s)) return rc;   // before the copies: a finished env reports its new episode's first observation
+    // Device -> host: one DMA per run of outputs that is contiguous on BOTH sides (the host package lays the
+    // five output arrays out back to back in one device slab and one pinned slab, so a step's results travel
+    // in a single transfer -- SURVEY 8(f1): "one D2H"); separate arrays still get a copy each.
+    struct Seg { char* dst; const char* src; size_t n; };
+    Seg seg[5];
+    int ns = 0;
+    if (obs) seg[ns++] = {(char*)obs, (const char*)sim->K.obs, (size_t)z.obs};
+    if (rewards) seg[ns++] = {(char*)rewards, (const char*)sim->K.rewards, (size_t)z.rewards};
+    if (nn_idx && sim->K.nn_idx) seg[ns++] = {(char*)nn_idx, (const char*)sim->K.nn_idx, (size_t)z.nn_idx};
+    if (collided) seg[ns++] = {(char*)collided, (const char*)sim->K.collided, (size_t)z.collided};
+    if (done) seg[ns++] = {(char*)done, (const char*)sim->K.done, (size_t)z.done};
+    for (int i = 1; i < ns; ++i)   // by device address
+        for (int j = i; j > 0 && seg[j].src < seg[j - 1].src; --j) { Seg t = seg[j]; seg[j] = seg[j - 1]; seg[j - 1] = t; }
+    for (int i = 0; i < ns;) {
+        size_t n = seg[i].n;
+        int j = i + 1;
+        // the next array starts within 256 bytes of this one's end (alignment padding) at the same offset on both sides
+        while (j < ns && seg[j].src >= seg[i].src + n && seg[j].src - (seg[i].src + n) < 256 &&
+               seg[j].dst - seg[i].dst == seg[j].src - seg[i].src) {
+            n = (size_t)(seg[j].src - seg[i].src) + seg[j].n;
+            ++j;
+        }
+        CU(cudaMemcpyAsync(seg[i].dst, seg[i].src, n, cudaMemcpyDeviceToHost, s));
+        i = j;
+    }
+    sim->host_dirty = 1;
     return MACM_OK;
 }
 
@@ -425,6 +590,7 @@ extern "C" int macm_host_sync(macm_sim* sim)
 {
     if (!sim) return MACM_E_INVALID;
     if (sim->hstream) CU(cudaStreamSynchronize(sim->hstream));
+    sim->host_dirty = 0;
     return MACM_OK;
 }
 

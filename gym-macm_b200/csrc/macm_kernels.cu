@@ -871,9 +871,45 @@ __device__ __noinline__ uint32_t bot_action(const SimConst& P, const Rollout& R,
             if (!(tn.x < 1.0f)) { a2 = (uint32_t)(th_sign + 1.0f); a0 = (uint32_t)(ahead + 1.0f); }
             break;
         }
+        case MACM_BOT_CIRCLE: {
+            const uint64_t gi = (uint64_t)env * P.N + i;
+            const Philox r(R.seed, gi + (uint64_t)P.env_base * P.N, 3u, (uint32_t)step);
+            a0 = 2; a2 = (r.c[0] >> 31) ? 2u : 1u;
+            break;
+        }
         default: break;
     }
     return a0 | (a1 << 8) | (a2 << 16) | (a3 << 24);
+}
+
+// The combat actor (bots.py:3-16) inside a rollout: agent i's observation row (combat.py:206-227) is recomputed
+// from the staged positions and angles with the arithmetic of tdm_observe, so the choice is the one
+// macm_bot_kernel makes from the `obs` buffer: nearest enemy (lowest index among equal r), turn towards it,
+// walk when it is within +-36 degrees, strike inside 3 m.
+__device__ __noinline__ uint32_t combat_action(const float2* pos, const float* angs, const uint8_t* team, int N,
+                                               uint2 alive, int i)
+{
+    uint32_t a0 = 1, a2 = 1, a3 = 0;
+    if (i < N && bit_of(alive, i)) {
+        const float2 p = pos[i];
+        const int ti = team[i];
+        float br = 0.0f, bdx = 0.0f, bdy = 0.0f;
+        bool found = false;
+        for (int j = 0; j < N; ++j) {
+            if (j == i || !bit_of(alive, j) || team[j] == ti) continue;
+            const float2 q = pos[j];
+            const float dx = q.x - p.x, dy = q.y - p.y;
+            const float r = out_sqrtf(dx * dx + dy * dy);
+            if (!found || r < br) { br = r; bdx = dx; bdy = dy; found = true; }
+        }
+        if (found) {
+            const float th = wrap_pi_f(fast_atan2f(bdy, bdx) - angs[i]);
+            a0 = (fabs((double)th) < NP_PI / 5) ? 2u : 1u;
+            a2 = th > 0.0f ? 2u : (th < 0.0f ? 0u : 1u);
+            a3 = br < 3.0f ? 1u : 0u;
+        }
+    }
+    return a0 | (1u << 8) | (a2 << 16) | (a3 << 24);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1035,6 +1071,19 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
     // they share every fetched line.
     if (R.sync() > 0 && ks > 0 && (ks % R.sync()) == 0) __syncthreads();
     g.sync();   // the previous step's observation pass has finished reading the staging arrays
+    uint2 alive0 = make_uint2(0u, 0u);   // (combat actor) who is in the observation the actors decide on
+    if (ROLL && TDM && R.policy() == MACM_BOT_COMBAT) {
+        if (ks == 0) {   // later steps: positions and angles are staged since the previous step's phases 7 and 11
+#pragma unroll
+            for (int s = 0; s < APL; ++s) { pos[g.gl + s * G] = c[s]; S.ang()[g.gl + s * G] = ang[s]; }
+        }
+#pragma unroll
+        for (int s = 0; s < APL; ++s) {
+            const unsigned bm = g.ballot(was_alive[s]);
+            if (s == 0) alive0.x = bm; else alive0.y = bm;
+        }
+        g.sync();
+    }
 #pragma unroll
     for (int s = 0; s < APL; ++s) {
         const int i = g.gl + s * G;
@@ -1051,6 +1100,8 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
                 const uint32_t* aw = reinterpret_cast<const uint32_t*>(actions) + (size_t)ks * EN + gi;
                 act_raw[s] = *aw;
                 if (!last) asm volatile("prefetch.global.L2 [%0];" ::"l"(aw + EN));
+            } else if (TDM && R.policy() == MACM_BOT_COMBAT) {
+                act_raw[s] = combat_action(pos, S.ang(), P.team, N, alive0, i);
             } else {
                 act_raw[s] = bot_action(P, R_, reinterpret_cast<const float2*>(S.nw())[i], env, i, step_cnt);
             }
@@ -1691,9 +1742,12 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
 #endif
 }
 
-// get_obs() alone
-template <int G, int APL, int KIND>
-__global__ void __launch_bounds__(128) macm_observe_kernel(const __grid_constant__ SimConst P)
+// get_obs() alone; with RESET, first a new episode for the envs selected by `mask` (null: the bound `done`
+// buffer) and nothing at all for the others -- macm_reset_masked: the reference's env.reset() (mvmnt.py:224-233,
+// combat.py:229-239) for the envs that are done (mvmnt.py:134-136, combat.py:171-182).
+template <int G, int APL, int KIND, bool RESET>
+__global__ void __launch_bounds__(128) macm_observe_kernel(const __grid_constant__ SimConst P, const uint8_t* __restrict__ mask,
+                                                           const __grid_constant__ SampleConst sc)
 {
     constexpr int NC = G * APL;
     constexpr int GPW = 32 / G;
@@ -1705,6 +1759,39 @@ __global__ void __launch_bounds__(128) macm_observe_kernel(const __grid_constant
     EnvS<NC> S;
     S.TC = P.TC;
     S.base = smem_raw + (size_t)slot_in_block * Lay<NC>::bytes(P.TC);
+    if (RESET) {
+        if (!(mask ? mask[env] : P.done[env])) return;   // the whole group leaves together
+        // episode counter of the env: bits 8.. of its flag word; keys the draws so that episodes differ
+        const uint32_t episode = ((uint32_t)P.env_state[env].y >> MACM_ENV_EPISODE_SHIFT) + 1u;
+        const float r = P.radius;
+#pragma unroll
+        for (int s = 0; s < APL; ++s) {
+            const int i = g.gl + s * G;
+            if (i >= P.N) continue;
+            const size_t gi = (size_t)env * P.N + i;
+            float x, y, a;
+            sample_agent(P, sc, gi + (uint64_t)P.env_base * P.N, i, episode, x, y, a);
+            // body creation (mvmnt.py:70-75): at rest, awake, fat AABB = tight +- b2_aabbExtension
+            P.posvel[gi] = make_float4(x, y, 0.0f, 0.0f);
+            P.angsleep[gi] = make_float2(a, 0.0f);
+            P.fat[gi] = make_float4((x - r) - B2_AABB_EXTENSION, (y - r) - B2_AABB_EXTENSION,
+                                    (x + r) + B2_AABB_EXTENSION, (y + r) + B2_AABB_EXTENSION);
+            P.rewards[gi] = 0.0f;
+            P.collided[gi] = 0;
+            if (KIND == MACM_ENV_TDM)
+                P.tdm[gi] = make_float4(P.init_health, __int_as_float(0), __int_as_float(0), __int_as_float(1));
+        }
+        if (KIND != MACM_ENV_TDM)
+            for (int t = g.gl; t < P.T; t += G)
+                const_cast<float2*>(P.targets)[(size_t)env * P.T + t] =
+                    sample_target(sc, (uint64_t)(env + P.env_base) * P.T + t, episode);
+        if (g.gl == 0) {
+            P.c_cnt[env] = 0;
+            P.env_state[env] = make_int4(0, MACM_ENV_FRESH | (int)(episode << MACM_ENV_EPISODE_SHIFT), 0, -1);
+        }
+        __threadfence_block();
+        g.sync();   // the group's stores (targets) are visible to its lanes below
+    }
     float ang[APL];
     uint2 alive = make_uint2(0u, 0u);
 #pragma unroll
@@ -1716,7 +1803,13 @@ __global__ void __launch_bounds__(128) macm_observe_kernel(const __grid_constant
         ang[s] = P.angsleep[gi].x;
         S.pos()[i] = ok ? make_float2(pv.x, pv.y) : make_float2(3.0e30f, 3.0e30f);
         S.ang()[i] = ang[s];
-        if (KIND != MACM_ENV_TDM) S.tgt()[i] = P.targets[(size_t)env * P.T + P.target_idx[ok ? i : 0]];
+        if (KIND != MACM_ENV_TDM) {
+            const float2* tg = P.targets + (size_t)env * P.T + P.target_idx[ok ? i : 0];
+            float2 tv;
+            if (RESET) asm volatile("ld.volatile.global.v2.f32 {%0, %1}, [%2];" : "=f"(tv.x), "=f"(tv.y) : "l"(tg));
+            else tv = *tg;
+            S.tgt()[i] = tv;
+        }
         bool al = ok;
         if (KIND == MACM_ENV_TDM) al = ok && (__float_as_int(P.tdm[gi].w) & 1);
         const unsigned bm = g.ballot(al);
@@ -1757,7 +1850,7 @@ cudaError_t launch_one(const SimConst& P, const LaunchCfg& cfg, const void* acti
                        bool observe_only)
 {
     if (observe_only) {
-        macm_observe_kernel<G, APL, KIND><<<cfg.obs_blocks, 128, cfg.obs_smem_bytes, s>>>(P);
+        macm_observe_kernel<G, APL, KIND, false><<<cfg.obs_blocks, 128, cfg.obs_smem_bytes, s>>>(P, nullptr, SampleConst{});
         return cudaGetLastError();
     }
     // the step kernel is launched with programmatic stream serialization: it may become resident
@@ -1781,6 +1874,13 @@ cudaError_t launch_one(const SimConst& P, const LaunchCfg& cfg, const void* acti
 }
 
 template <int G, int APL, int KIND>
+cudaError_t reset_masked_one(const SimConst& P, const LaunchCfg& cfg, const uint8_t* mask, const SampleConst& sc, cudaStream_t s)
+{
+    macm_observe_kernel<G, APL, KIND, true><<<cfg.obs_blocks, 128, cfg.obs_smem_bytes, s>>>(P, mask, sc);
+    return cudaGetLastError();
+}
+
+template <int G, int APL, int KIND>
 cudaError_t prepare_one(const LaunchCfg& cfg, int* blocks_per_sm)
 {
     cudaError_t e = cudaFuncSetAttribute(macm_step_kernel<G, APL, KIND, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1790,7 +1890,10 @@ cudaError_t prepare_one(const LaunchCfg& cfg, int* blocks_per_sm)
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(macm_step_kernel<G, APL, KIND, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.smem_bytes);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(macm_observe_kernel<G, APL, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(macm_observe_kernel<G, APL, KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             cfg.obs_smem_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(macm_observe_kernel<G, APL, KIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              cfg.obs_smem_bytes);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, macm_step_kernel<G, APL, KIND, 0>, cfg.threads,
@@ -1881,6 +1984,14 @@ cudaError_t macm_launch_step(const SimConst& P, const LaunchCfg& cfg, const void
 cudaError_t macm_launch_observe(const SimConst& P, const LaunchCfg& cfg, cudaStream_t s)
 {
 #define CALL(G_, A_, K_) launch_one<G_, A_, K_>(P, cfg, nullptr, Rollout{}, s, true)
+    DISPATCH_SHAPE(CALL)
+#undef CALL
+}
+
+cudaError_t macm_launch_reset_masked(const SimConst& P, const LaunchCfg& cfg, const uint8_t* mask, const SampleConst& sc,
+                                     cudaStream_t s)
+{
+#define CALL(G_, A_, K_) reset_masked_one<G_, A_, K_>(P, cfg, mask, sc, s)
     DISPATCH_SHAPE(CALL)
 #undef CALL
 }

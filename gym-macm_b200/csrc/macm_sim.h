@@ -62,6 +62,12 @@ struct Rollout {
     float* obs; int* nn_idx; float* rewards; uint8_t* collided; uint8_t* done;
 };
 
+// Initial-state distributions (mvmnt.py:48-52,62-64; combat.py:84-86) and the key of the counter-based draws.
+struct SampleConst {
+    unsigned long long seed;
+    double spread, sx, sy, tmin, tmax, width, height;
+};
+
 struct LaunchCfg {
     int G, APL, envs_per_block, threads, blocks, smem_bytes;   // the step kernel
     int per_env_bytes;                                          // shared memory of one env
@@ -93,6 +99,32 @@ struct Philox {
         return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
     }
 };
+
+// One agent's initial state (mvmnt.py:62-64 / combat.py:84-86) and one target (mvmnt.py:48-52): pure functions of
+// (seed, GLOBAL agent / target index, episode) -- the same draws whatever kernel or launch shape asks for them.
+__device__ __forceinline__ void sample_agent(const SimConst& P, const SampleConst& sc, uint64_t gidx, int i,
+                                             uint32_t episode, float& x, float& y, float& a)
+{
+    const Philox r(sc.seed, gidx, 0u, 2u * episode);
+    const Philox r2(sc.seed, gidx, 0u, 2u * episode + 1u);
+    double dx, dy;
+    if (P.kind == MACM_ENV_FLOCK) {
+        dx = sc.spread * (r.u53(0) - 0.5) + sc.sx;   // mvmnt.py:62-63
+        dy = sc.spread * (r.u53(1) - 0.5) + sc.sy;
+    } else {
+        dx = r.u53(0) * ((double)P.team[i] + sc.width / 2);  // combat.py:84-85
+        dy = r.u53(1) * sc.height;
+    }
+    x = (float)dx; y = (float)dy;
+    a = (float)((-1.0 + 2.0 * r2.u53(0)) * NP_PI);   // random.uniform(-1, 1) * np.pi
+}
+__device__ __forceinline__ float2 sample_target(const SampleConst& sc, uint64_t gtidx, uint32_t episode)
+{
+    const Philox r(sc.seed, gtidx, 1u, 2u * episode);
+    const double ang = 2 * NP_PI * r.u53(0);              // mvmnt.py:50-52
+    const double dist = sc.tmin + r.u53(1) * (sc.tmax - sc.tmin);
+    return make_float2((float)(dist * cos(ang)), (float)(dist * sin(ang)));
+}
 #endif
 
 // implemented in macm_kernels.cu
@@ -101,6 +133,9 @@ cudaError_t macm_prepare_kernels(const SimConst& P, const LaunchCfg& cfg, int* b
 cudaError_t macm_launch_step(const SimConst& P, const LaunchCfg& cfg, const void* actions, const Rollout& R, cudaStream_t s);
 cudaError_t macm_launch_observe(const SimConst& P, const LaunchCfg& cfg, cudaStream_t s);
 cudaError_t macm_launch_reset(const SimConst& P, cudaStream_t s);
-cudaError_t macm_launch_sample(const SimConst& P, uint64_t seed, double start_spread, double start_x, double start_y,
-                               double tmin, double tmax, double width, double height, cudaStream_t s);
+cudaError_t macm_launch_reset_masked(const SimConst& P, const LaunchCfg& cfg, const uint8_t* mask, const SampleConst& sc,
+                                     cudaStream_t s);
+cudaError_t macm_launch_sample(const SimConst& P, const SampleConst& sc, cudaStream_t s);
+cudaError_t macm_launch_overflow_count(const SimConst& P, int* d_out2, cudaStream_t s);
+cudaError_t macm_launch_pack_actions(const void* src, int elem_bytes, int width, uint64_t n_agents, void* out, cudaStream_t s);
 cudaError_t macm_launch_bot(const SimConst& P, int policy, uint64_t seed, void* actions_out, cudaStream_t s);

@@ -13,7 +13,10 @@ ACTION = {"discrete": 0, "continuous": 1}
 COORD = {"polar": 0, "cartesian": 1}
 DAMPING = {"taylor": 0, "pade": 1, "2.3.0": 0, "2.3.1": 1}
 ENV_FRESH, ENV_CONTACT_OVERFLOW, ENV_TOUCH_OVERFLOW = 1, 2, 4
-BOTS = {"idle": 0, "forward": 1, "rotate": 2, "diag": 3, "flock": 4, "random": 5, "combat": 6}
+BOTS = {"idle": 0, "forward": 1, "rotate": 2, "diag": 3, "flock": 4, "random": 5, "combat": 6, "circle": 7}
+FLAG_REPAIR_MOV_COOLDOWN, FLAG_AUTO_RESET = 1, 2
+ENV_EPISODE_SHIFT = 8
+ABI_VERSION = 3
 
 i32, f64, u64 = C.c_int32, C.c_double, C.c_uint64
 
@@ -61,7 +64,8 @@ class MacmRolloutOut(C.Structure):
 
 EXPORTS = ("macm_abi_version", "macm_strerror", "macm_last_cuda_error", "macm_params_default", "macm_create",
            "macm_destroy", "macm_get_buffer_sizes", "macm_get_launch_info", "macm_bind", "macm_reset",
-           "macm_sample_reset", "macm_step", "macm_rollout", "macm_observe", "macm_bot_actions", "macm_step_host", "macm_step_host_async", "macm_host_sync",
+           "macm_sample_reset", "macm_reset_masked", "macm_set_auto_reset_seed", "macm_overflow_count", "macm_pack_actions",
+           "macm_step", "macm_rollout", "macm_observe", "macm_bot_actions", "macm_step_host", "macm_step_host_async", "macm_host_sync",
            "macm_host_alloc",
            "macm_host_free", "macm_launch_count", "macm_set_trace", "macm_enable_peer_access", "macm_ipc_open",
            "macm_ipc_close", "macm_device_alloc", "macm_device_free")
@@ -96,6 +100,10 @@ def lib():
         L.macm_bind.argtypes = [vp, C.POINTER(MacmBuffers)]
         L.macm_reset.argtypes = [vp, vp]
         L.macm_sample_reset.argtypes = [vp, u64, vp]
+        L.macm_reset_masked.argtypes = [vp, vp, u64, vp]
+        L.macm_set_auto_reset_seed.argtypes = [vp, u64]
+        L.macm_overflow_count.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), vp]
+        L.macm_pack_actions.argtypes = [vp, vp, i32, i32, vp, vp]
         L.macm_step.argtypes = [vp, vp, vp]
         L.macm_rollout.argtypes = [vp, vp, C.c_int32, C.c_int32, u64, C.POINTER(MacmRolloutOut), vp]
         L.macm_observe.argtypes = [vp, vp]
@@ -113,7 +121,7 @@ def lib():
         L.macm_ipc_close.argtypes = [vp]
         L.macm_device_alloc.argtypes = [C.c_int, u64, C.POINTER(vp), C.c_char_p]
         L.macm_device_free.argtypes = [vp]
-        if L.macm_abi_version() != 2:
+        if L.macm_abi_version() != ABI_VERSION:
             raise MacmError("libmacm.so ABI version mismatch")
         _lib = L
     return _lib

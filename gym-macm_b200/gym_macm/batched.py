@@ -50,6 +50,8 @@ def flock_params(settings, n_envs, n_agents, n_targets):
     p.start_x, p.start_y = float(settings.start_point[0]), float(settings.start_point[1])
     p.target_mindist, p.target_maxdist = float(settings.target_mindist), float(settings.target_maxdist)
     p.env_index_base = int(settings.env_index_base)
+    if settings.auto_reset:
+        p.flags |= _lib.FLAG_AUTO_RESET
     return p
 
 
@@ -69,7 +71,8 @@ def tdm_params(settings, n_envs, n_agents):
     p.agent_force = float(settings.agent_force)
     p.agent_rotation_speed = float(settings.agent_rotation_speed)
     p.time_limit = float(settings.time_limit)
-    p.flags = 1 if settings.repair_mov_cooldown else 0
+    p.flags = (_lib.FLAG_REPAIR_MOV_COOLDOWN if settings.repair_mov_cooldown else 0) | \
+              (_lib.FLAG_AUTO_RESET if settings.auto_reset else 0)
     p.cooldown_atk, p.cooldown_mov_penalty = float(settings.cooldown_atk), float(settings.cooldown_mov_penalty)
     p.melee_range, p.melee_dmg = float(settings.melee_range), float(settings.melee_dmg)
     p.percent_mov_penalty, p.init_health = float(settings.percent_mov_penalty), float(settings.init_health)
@@ -81,6 +84,8 @@ def tdm_params(settings, n_envs, n_agents):
 class Engine(object):
     """A macm_sim handle plus the torch tensors bound to it."""
 
+    OUTPUTS = ("obs", "rewards", "done", "nn_idx", "collided")   # order inside the output slab
+
     _DTYPES = dict(posvel="float32", angsleep="float32", fat="float32", contact_ab="int32", contact_imp="float32",
                    contact_count="int32", env_state="int32", targets="float32", target_idx="uint8",
                    tdm_state="float32", team="uint8", obs="float32", nn_idx="int32", rewards="float32",
@@ -89,6 +94,7 @@ class Engine(object):
     def __init__(self, params, device=None):
         torch = _torch()
         self._h = None
+        self._pinned = None
         L = _lib.lib()  # raises when libmacm.so has not been built
         if not torch.cuda.is_available():
             raise _lib.MacmError("gym_macm needs a CUDA device: the simulator is CUDA-only and has no CPU fallback")
@@ -101,7 +107,13 @@ class Engine(object):
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             torch.cuda.init()
-            _lib.check(L.macm_create(C.byref(h), C.byref(params), self.device.index))
+            rc = L.macm_create(C.byref(h), C.byref(params), self.device.index)
+        if rc != 0:   # a handle returned with an error only carries the CUDA error text
+            try:
+                _lib.check(rc, h if h else None)
+            finally:
+                if h:
+                    L.macm_destroy(h)
         self._h = h
         self.sizes = _lib.MacmBufferSizes()
         _lib.check(L.macm_get_buffer_sizes(h, C.byref(self.sizes)))
@@ -114,18 +126,34 @@ class Engine(object):
                       team=(N,), obs=(E, N, D), nn_idx=(E, N), rewards=(E, N), collided=(E, N), done=(E,))
         self.t = {}
         bufs = _lib.MacmBuffers()
+        # The per-step outputs live back to back in ONE device slab (each array 16-byte aligned), in the order
+        # a learner asks for them; the pinned host mirror (pinned()) has the same layout, so macm_step_host moves
+        # a step's results in a single device->host transfer.
+        self._out_layout, off = {}, 0
+        for name in self.OUTPUTS:
+            nbytes = getattr(self.sizes, name)
+            if nbytes:
+                self._out_layout[name] = (off, nbytes)
+                off = (off + nbytes + 15) // 16 * 16
+        self._out_bytes = off
+        slab = torch.zeros(off, dtype=torch.uint8, device=self.device)
+        self._out_slab = slab
         for name in _lib.BUFFER_NAMES:
             nbytes = getattr(self.sizes, name)
             if nbytes == 0:
                 continue
-            ten = torch.zeros(shapes[name], dtype=getattr(torch, self._DTYPES[name]), device=self.device)
+            dt = getattr(torch, self._DTYPES[name])
+            if name in self._out_layout:
+                o = self._out_layout[name][0]
+                ten = slab[o:o + nbytes].view(dt).view(shapes[name])
+            else:
+                ten = torch.zeros(shapes[name], dtype=dt, device=self.device)
             assert ten.numel() * ten.element_size() == nbytes, (name, ten.shape, nbytes)
             self.t[name] = ten
             setattr(bufs, name, ten.data_ptr())
         _lib.check(L.macm_bind(h, C.byref(bufs)), h)
         self.E, self.N, self.T, self.C, self.obs_dim = E, N, T, Cc, D
         self.action_bytes = self.sizes.action_bytes
-        self._pinned = None
 
     def close(self):
         h, self._h = self._h, None
@@ -151,6 +179,36 @@ class Engine(object):
 
     def sample_reset(self, seed):
         _lib.check(_lib.lib().macm_sample_reset(self._h, C.c_uint64(int(seed) & (2 ** 64 - 1)), self._stream()), self._h)
+
+    def reset_masked(self, mask=None, seed=0, stream=None):
+        """macm_reset_masked: a new episode for the envs whose `mask` entry (uint8 / bool [E], device) is set;
+        mask=None selects the envs whose `done` flag is set."""
+        ptr = None
+        if mask is not None:
+            torch = _torch()
+            if mask.dtype == torch.bool:
+                mask = mask.to(torch.uint8)
+            mask = mask.to(self.device).contiguous()
+            assert mask.dtype == torch.uint8 and mask.numel() == self.E
+            ptr = C.c_void_p(mask.data_ptr())
+        _lib.check(_lib.lib().macm_reset_masked(self._h, ptr, C.c_uint64(int(seed) & (2 ** 64 - 1)), self._stream(stream)),
+                   self._h)
+
+    def set_auto_reset_seed(self, seed):
+        _lib.check(_lib.lib().macm_set_auto_reset_seed(self._h, C.c_uint64(int(seed) & (2 ** 64 - 1))), self._h)
+
+    def overflow_count(self):
+        """(envs with dropped contacts, envs whose solver stage overflowed) -- synchronises the stream."""
+        a, b = C.c_int32(0), C.c_int32(0)
+        _lib.check(_lib.lib().macm_overflow_count(self._h, C.byref(a), C.byref(b), self._stream()), self._h)
+        return int(a.value), int(b.value)
+
+    def pack_actions(self, src, out):
+        """Integer tensor [E,N,3|4] on the device -> uint8 [E,N,4] action words (one small kernel of the library)."""
+        src = src.contiguous()
+        _lib.check(_lib.lib().macm_pack_actions(self._h, C.c_void_p(src.data_ptr()), int(src.element_size()),
+                                                int(src.shape[-1]), C.c_void_p(out.data_ptr()), self._stream()), self._h)
+        return out
 
     def step(self, actions, stream=None):
         """One step on torch's current stream, or on `stream` (a torch.cuda.Stream): independent batches stepped
@@ -188,9 +246,10 @@ class Engine(object):
             adt = torch.uint8 if self.action_bytes == 4 else torch.float32
             ashape = (self.E, self.N, 4) if self.action_bytes == 4 else (self.E, self.N, 2)
             p = dict(actions=torch.zeros(ashape, dtype=adt).pin_memory())
-            for name in ("obs", "rewards", "nn_idx", "collided", "done"):
-                if name in self.t:
-                    p[name] = torch.zeros(self.t[name].shape, dtype=self.t[name].dtype).pin_memory()
+            slab = torch.zeros(self._out_bytes, dtype=torch.uint8).pin_memory()   # same layout as the device slab
+            p["_slab"] = slab
+            for name, (o, nbytes) in self._out_layout.items():
+                p[name] = slab[o:o + nbytes].view(self.t[name].dtype).view(self.t[name].shape)
             self._pinned = p
         return self._pinned
 
@@ -217,7 +276,49 @@ class Engine(object):
         return int(_lib.lib().macm_launch_count(self._h))
 
 
-class BatchedFlock(object):
+class _BatchedCommon(object):
+    """What BatchedFlock and BatchedTDM share: episode bookkeeping, overflow reporting, renderer export."""
+
+    @property
+    def episode(self):
+        """How many times each env has been reset by reset_done / auto_reset (int32 [E])."""
+        return self.engine.t["env_state"][:, 1] >> _lib.ENV_EPISODE_SHIFT
+
+    @property
+    def overflowed(self):
+        """bool [E]: the env ran out of contact capacity (`max_contacts`: newest pairs dropped; `max_touching`, at
+        most 240: the solver skipped the excess) at some step since its last reset -- from that step on its
+        results differ from the reference's.  Sticky until the env is reset."""
+        return (self.engine.t["env_state"][:, 1] & (_lib.ENV_CONTACT_OVERFLOW | _lib.ENV_TOUCH_OVERFLOW)) != 0
+
+    def overflow_count(self):
+        """(envs with dropped contacts, envs with a truncated solver stage); one small kernel + a 8-byte read."""
+        return self.engine.overflow_count()
+
+    def _check_overflow(self):
+        if self.settings.check_overflow:
+            c, t = self.engine.overflow_count()
+            if c or t:
+                raise _lib.MacmError("contact capacity overflow: %d envs dropped contacts (max_contacts=%d), %d envs "
+                                     "exceeded the solver stage (max_touching=%d, limit 240); results of those envs "
+                                     "differ from the reference's" % (c, self.engine.C, t, self.engine.sizes.max_touching))
+
+    def reset_done(self, mask=None, seed=0):
+        """The reference's env.reset() (mvmnt.py:224-233, combat.py:229-239) for SOME envs of the batch: those
+        whose `mask` entry is set, or with mask=None those that are done (time limit, mvmnt.py:134-136; one team
+        left, combat.py:171-182).  Fresh states drawn on the device, keyed by (seed, env, agent, episode)."""
+        self.engine.reset_masked(mask, seed)
+        return self.obs
+
+    def render_state(self, env=0):
+        """One env of the batch as the objects the reference's CPU renderer reads
+        (backends/pyglet_framework.py:122-180: `body.transform`, `body.userData.color`, fixtures' circle shape;
+        `gui_objects` as filled by mvmnt.py:54-57): see gym_macm.render.  A device->host read of ~1 KB."""
+        from gym_macm import render
+        return render.export(self, int(env))
+
+
+class BatchedFlock(_BatchedCommon):
     """E independent Flock environments (gym_macm/envs/mvmnt.py) on one GPU.
 
     Same constructor keywords as the reference (`n_agents`, `actors`, `colors`, `targets`, any
@@ -329,8 +430,10 @@ class BatchedFlock(object):
         E, N = self.engine.E, self.engine.N
         if self._act4 is None:
             self._act4 = torch.zeros((E, N, 4), dtype=torch.uint8, device=self.device)
-        self._act4[..., 0:3] = torch.as_tensor(actions, device=self.device).reshape(E, N, 3)
-        return self._act4
+        a = torch.as_tensor(actions, device=self.device)
+        if a.dtype.is_floating_point or a.dtype == torch.bool:
+            a = a.to(torch.uint8)
+        return self.engine.pack_actions(a.reshape(E, N, -1), self._act4)
 
     def step(self, actions):
         torch = _torch()
@@ -343,6 +446,7 @@ class BatchedFlock(object):
         else:
             a = torch.as_tensor(actions, dtype=torch.float32, device=self.device).reshape(E, N, 2).contiguous()
         self.engine.step(a)
+        self._check_overflow()
         return self.obs, self.engine.t["rewards"]
 
     def rollout(self, actions=None, n_steps=None, policy="random", seed=0, want=("obs", "nn_idx", "rewards", "collided", "done"),
@@ -379,6 +483,7 @@ class BatchedFlock(object):
         if out is None:
             out = self.engine.rollout_buffers(K, want)
         self.engine.rollout(a, K, pol, seed, out)
+        self._check_overflow()
         return out
 
     def step_host(self, actions):
@@ -410,7 +515,7 @@ class BatchedFlock(object):
         self.engine.close()
 
 
-class BatchedTDM(object):
+class BatchedTDM(_BatchedCommon):
     """E independent team-deathmatch environments (gym_macm/envs/combat.py) on one GPU, with the
     repaired semantics of SURVEY.md Appendix B (the reference class cannot be constructed as
     shipped).  `n_agents=[15, 15, 15]` gives three teams; agent index = team-major order, the
@@ -514,9 +619,12 @@ class BatchedTDM(object):
                 and a.is_contiguous()):
             if self._act4 is None:
                 self._act4 = torch.zeros((E, N, 4), dtype=torch.uint8, device=self.device)
-            self._act4.copy_(torch.as_tensor(actions, device=self.device).reshape(E, N, 4))
-            a = self._act4
+            src = torch.as_tensor(actions, device=self.device)
+            if src.dtype.is_floating_point or src.dtype == torch.bool:
+                src = src.to(torch.uint8)
+            a = self.engine.pack_actions(src.reshape(E, N, 4), self._act4)
         self.engine.step(a)
+        self._check_overflow()
         return self.obs, self.engine.t["rewards"]
 
     def bot_actions(self, policy="random", seed=0, out=None):

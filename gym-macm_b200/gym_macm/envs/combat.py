@@ -13,6 +13,7 @@ import numpy as np
 
 from gym_macm import spaces
 from gym_macm.batched import BatchedTDM, _as_list
+from gym_macm.envs.mvmnt import check_capacity
 
 try:  # pragma: no cover
     import gym as _gym
@@ -90,6 +91,9 @@ class TDM(_Base):
         if render is True:
             raise NotImplementedError("rendering stays with the reference's CPU backends")
         n_agents = _as_list(n_agents)
+        nn = sum(n_agents)
+        kwargs.setdefault("max_contacts", max(1, nn * (nn - 1) // 2))   # one world: full capacity (see mvmnt.Flock)
+        kwargs.setdefault("max_touching", 240)
         self._batch = BatchedTDM(1, n_agents=n_agents, device=device, seed=None, **kwargs)
         self.settings = self._batch.settings
         self.done = False
@@ -145,6 +149,7 @@ class TDM(_Base):
         a = torch.from_numpy(encode_tdm_actions(actions, self._ids, alive)[None])
         out = self._batch.engine.step_host(a, want=("rewards", "collided", "done"))
         self._cache = None
+        check_capacity(self._batch)
         rewards = {aid: (-1 if out["rewards"][0, k] < 0 else 0) for k, aid in enumerate(self._ids)
                    if self._tdm()[3][k]}
         self.obs = self.get_obs(observe=False)
@@ -206,6 +211,10 @@ class TDM(_Base):
 
     def CheckKeys(self, *args):
         pass
+
+    def render_state(self):
+        """The objects the reference's CPU renderer reads (pyglet_framework.py:122-180), see gym_macm.render."""
+        return self._batch.render_state(0)
 
     def quit(self):
         return

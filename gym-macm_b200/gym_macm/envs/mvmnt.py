@@ -56,6 +56,15 @@ class Agent(object):
         self.color = self._color
 
 
+def check_capacity(batch):
+    """The dict API never returns results that silently differ from the reference's: a world that ran out of
+    contact capacity (more than 240 touching contacts at once) raises."""
+    from gym_macm._lib import ENV_CONTACT_OVERFLOW, ENV_TOUCH_OVERFLOW, MacmError
+    if int(batch.state["env_state"][0, 1]) & (ENV_CONTACT_OVERFLOW | ENV_TOUCH_OVERFLOW):
+        raise MacmError("the world holds more contacts than the simulator's capacity (max_contacts=%d, max_touching=%d)"
+                        % (batch.engine.C, batch.engine.sizes.max_touching))
+
+
 # ---- pure marshalling helpers (no device needed; covered by the CPU tests) --------------------
 def encode_discrete_actions(actions, ids, width=3):
     """{id: [a0, a1, a2(, a3)]} -> uint8 [N, 4] in agent order."""
@@ -101,6 +110,11 @@ class Flock(_Base):
 
     def __init__(self, n_agents=[10], actors=None, colors=None, targets=None, device=None, **kwargs):
         n_agents = _as_list(n_agents)
+        # one world: room for every possible pair and the largest solver stage, so that a pile at the target
+        # cannot run out of contact capacity (a batch trades that for shared memory, see BatchedFlock.overflowed)
+        nn = sum(n_agents)
+        kwargs.setdefault("max_contacts", max(1, nn * (nn - 1) // 2))
+        kwargs.setdefault("max_touching", 240)
         self._batch = BatchedFlock(1, n_agents=n_agents, actors=actors, colors=colors, targets=targets,
                                    device=device, seed=None, **kwargs)
         self.settings = self._batch.settings
@@ -168,6 +182,7 @@ class Flock(_Base):
             a = torch.from_numpy(encode_continuous_actions(actions, self._ids)[None])
         out = self._batch.engine.step_host(a)
         self._cache = None
+        check_capacity(self._batch)
         rewards = rewards_to_dict(self._ids, out["rewards"][0].numpy(), out["collided"][0].numpy(),
                                   self.settings.reward_mode)
         self.time_passed += (1 / self.settings.hz)
@@ -225,6 +240,10 @@ class Flock(_Base):
 
     def BeginContact(self, agent1, agent2):
         pass
+
+    def render_state(self):
+        """The objects the reference's CPU renderer reads (pyglet_framework.py:122-180), see gym_macm.render."""
+        return self._batch.render_state(0)
 
     def quit(self):
         return

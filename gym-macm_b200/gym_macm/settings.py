@@ -64,6 +64,9 @@ class _EnvSettings(fwSettings):
         self.max_contacts = 0              # 0 = library default
         self.max_touching = 0
         self.env_index_base = 0            # global index of this batch's env 0 (gym_macm.dist shards)
+        # batched hosts only (the reference has one world and a broken reset()):
+        self.auto_reset = False            # an env whose `done` flag is set starts a new episode right after the step
+        self.check_overflow = False        # debug: step() raises when an env ran out of contact capacity
 
 
 class flockSettings(_EnvSettings):

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MACM_ABI_VERSION 2
+#define MACM_ABI_VERSION 3
 #define MACM_MAX_AGENTS 64   /* per environment (contact adjacency is a 64-bit row per agent) */
 #define MACM_MAX_TARGETS 16
 #define MACM_MAX_TEAMS 8
@@ -54,17 +54,21 @@ enum { MACM_COORD_POLAR = 0, MACM_COORD_CARTESIAN = 1 };
 enum { MACM_DAMPING_TAYLOR = 0, MACM_DAMPING_PADE = 1 };
 /* macm_params.flags */
 enum {
-    MACM_FLAG_REPAIR_MOV_COOLDOWN = 1 /* cooldown_mov_penalty counts down */
+    MACM_FLAG_REPAIR_MOV_COOLDOWN = 1, /* cooldown_mov_penalty counts down */
+    MACM_FLAG_AUTO_RESET = 2           /* every macm_step / macm_rollout launch is followed by macm_reset_masked(NULL):
+                                          envs whose `done` flag is set start a new episode (see macm_reset_masked) */
 };
-/* env_state[e][1] bits */
+/* env_state[e][1]: bits 0-2 flags, bits 8-31 the env's episode counter (incremented by macm_reset_masked) */
 enum {
     MACM_ENV_FRESH = 1,           /* world has new fixtures: FindNewContacts runs at the start of the next step */
-    MACM_ENV_CONTACT_OVERFLOW = 2,/* more live contacts than max_contacts: newest were dropped */
-    MACM_ENV_TOUCH_OVERFLOW = 4   /* more touching contacts than max_touching: solver skipped the excess */
+    MACM_ENV_CONTACT_OVERFLOW = 2,/* more live contacts than max_contacts: newest were dropped (sticky until reset) */
+    MACM_ENV_TOUCH_OVERFLOW = 4   /* more touching contacts than max_touching: solver skipped the excess (sticky) */
 };
+#define MACM_ENV_EPISODE_SHIFT 8
 /* scripted actors of test_scripts/bots.py, run on the device by macm_bot_actions */
 enum { MACM_BOT_IDLE = 0, MACM_BOT_FORWARD = 1, MACM_BOT_ROTATE = 2, MACM_BOT_DIAG = 3,
-       MACM_BOT_FLOCK = 4, MACM_BOT_RANDOM = 5, MACM_BOT_COMBAT = 6 };
+       MACM_BOT_FLOCK = 4, MACM_BOT_RANDOM = 5, MACM_BOT_COMBAT = 6 /* bots.py:3-16, TDM only */,
+       MACM_BOT_CIRCLE = 7 /* bots.py:31-35 */ };
 
 /*
  * Everything gym_macm/settings.py and the Agent classes hold that the hot path reads.
@@ -188,6 +192,24 @@ int macm_reset(macm_sim* sim, void* stream);
  * does what macm_reset does.  The reference draws from Python's unseeded `random`. */
 int macm_sample_reset(macm_sim* sim, uint64_t seed, void* stream);
 
+/* Per-env reset: a new episode for some envs of the batch, the others untouched -- the reference's `env.reset()`
+ * (mvmnt.py:224-233, combat.py:229-239; broken as shipped) applied to the envs a learner has
+ * seen finish (`done`: time limit mvmnt.py:134-136, one team left combat.py:171-182).
+ *   mask   device uint8 [E] (non-zero = reset this env), or NULL = the bound `done` buffer.
+ * A selected env gets fresh agent states and targets drawn from the reference's distributions (the draws of
+ * macm_sample_reset keyed by (seed, global env, agent, episode), episode = the env's reset count, so two
+ * episodes of one env differ and a batch is the same however it is sharded), then what macm_reset does for it:
+ * fat AABBs, no contacts, step_count 0, MACM_ENV_FRESH, cleared overflow bits, TDM health / cool-downs /
+ * alive, rewards and collided 0, the first observation of the new episode in `obs` / `nn_idx`.  `done` is
+ * left as it is (the learner reads it; the next step overwrites it).  One launch, no host synchronisation. */
+int macm_reset_masked(macm_sim* sim, const uint8_t* mask, uint64_t seed, void* stream);
+/* Seed of the resets that MACM_FLAG_AUTO_RESET appends to every step (default 0). */
+int macm_set_auto_reset_seed(macm_sim* sim, uint64_t seed);
+/* Device-side overflow summary: *contact_envs / *touching_envs receive how many envs currently carry
+ * MACM_ENV_CONTACT_OVERFLOW / MACM_ENV_TOUCH_OVERFLOW (results of such an env differ from the reference's from
+ * the overflowing step on).  Synchronises `stream`.  Either pointer may be NULL. */
+int macm_overflow_count(macm_sim* sim, int32_t* contact_envs, int32_t* touching_envs, void* stream);
+
 /* Replaces one Flock.step / TDM.step for every env (mvmnt.py:81-140, combat.py:104-184):
  * action decode -> ApplyForce, framework.Step -> b2World::Step(1/hz, velIters, posIters) +
  * ClearForces (cm_framework.py:213-224), get_rewards (mvmnt.py:160-179), time/done
@@ -213,8 +235,8 @@ typedef struct macm_rollout_out {
  * out->x[k] holds what buffer x held after call k.
  *   actions != NULL : [n_steps,E,N,4] uint8 (discrete) or [n_steps,E,N,2] float (continuous), device.
  *   actions == NULL : the actions=None mode (mvmnt.py:86-92): every agent's actor picks its action from
- *                     its own last observation, policy = MACM_BOT_IDLE..MACM_BOT_RANDOM as in macm_bot_actions
- *                     (MACM_BOT_FLOCK: Flock with polar coordinates), draws keyed by (seed, env, agent, step_count).
+ *                     its own last observation, policy = MACM_BOT_* as in macm_bot_actions (MACM_BOT_FLOCK: Flock
+ *                     with polar coordinates; MACM_BOT_COMBAT: TDM), draws keyed by (seed, env, agent, step_count).
  * With out == NULL or out->obs == NULL the observation pass only runs after the last step (action repeat /
  * frame skip); rewards of the intermediate steps are still available through out->rewards. */
 int macm_rollout(macm_sim* sim, const void* actions, int32_t n_steps, int32_t policy, uint64_t seed,
@@ -224,13 +246,21 @@ int macm_rollout(macm_sim* sim, const void* actions, int32_t n_steps, int32_t po
 int macm_observe(macm_sim* sim, void* stream);
 
 /* test_scripts/bots.py on the device: writes one action per agent from the current `obs`
- * buffer (`actions=None` mode, mvmnt.py:86-92).  MACM_BOT_RANDOM draws U{0,1,2}^3 (x U{0,1})
- * keyed by (seed, env, agent, step_count). */
+ * buffer (`actions=None` mode, mvmnt.py:86-92).  MACM_BOT_RANDOM draws U{0,1,2}^3 (x U{0,1}) and
+ * MACM_BOT_CIRCLE its coin keyed by (seed, env, agent, step_count); MACM_BOT_COMBAT (TDM) faces, approaches and
+ * strikes the nearest enemy of the agent's observation row (bots.py:3-16). */
 int macm_bot_actions(macm_sim* sim, int policy, uint64_t seed, void* actions_out, void* stream);
+
+/* Any little-endian integer array [E,N,width] (width 3 = a0 a1 a2, or 4 = + attack; elements of 1, 2, 4 or 8
+ * bytes, device memory) -> the uint8 [E,N,4] action words macm_step reads (actions dict -> array, mvmnt.py:94-101). */
+int macm_pack_actions(macm_sim* sim, const void* src, int32_t elem_bytes, int32_t width, void* actions_out, void* stream);
 
 /* The drop-in boundary with HOST buffers: copies `actions` host->device, steps, copies
  * obs / rewards / nn_idx / collided / done device->host (any of the outputs may be NULL) and
- * waits.  Pinned host memory (macm_host_alloc) makes the copies asynchronous DMA. */
+ * waits.  Pinned host memory (macm_host_alloc) makes the copies asynchronous DMA.  Outputs that lie back to
+ * back in device memory AND in host memory (same offsets, gaps under 256 bytes) travel in ONE transfer.
+ * The handle's stream is ordered after everything the other entry points enqueued for this handle before the
+ * call, and their later launches after it (events recorded at the hand-over, none between two steps). */
 int macm_step_host(macm_sim* sim, const void* actions, float* obs, float* rewards, int32_t* nn_idx,
                    uint8_t* collided, uint8_t* done);
 /* The same work enqueued on the handle's own stream without waiting: with pinned host buffers the

@@ -716,32 +716,51 @@ void oracle_destroy(OBatch* B)
 
 /* Fresh worlds, as Flock.__init__ / TDM.__init__ build them (mvmnt.py:61-76, combat.py:82-98):
  * pos/angle are float64 on the Python side and become float32 at the SWIG boundary. */
+static void reset_env(OBatch* B, int ei, const double* pos /*[N,2]*/, const double* angle /*[N]*/,
+                      const double* targets /*[T,2] or NULL*/, const uint8_t* target_idx /*[N] or NULL*/,
+                      const uint8_t* team /*[N] or NULL*/)
+{
+    int N = B->p.n_agents, T = B->p.n_targets;
+    OEnv* e = &B->e[ei];
+    ow_clear(&e->w);
+    for (int i = 0; i < N; ++i) {
+        ow_add_body(&e->w, (float)pos[i * 2], (float)pos[i * 2 + 1], (float)angle[i]);
+        if (target_idx) e->target_idx[i] = target_idx[i];
+        e->health[i] = B->p.init_health;
+        e->cd_atk[i] = 0.0;
+        e->cd_mov[i] = 0.0;
+        e->alive[i] = 1;
+        if (team) e->team[i] = team[i];
+    }
+    for (int t = 0; t < T; ++t)
+        if (targets) e->targets[t] = v2((float)targets[t * 2], (float)targets[t * 2 + 1]);
+    e->time_passed = 0.0;
+    e->done = 0;
+    e->winner = -1;
+    e->step_count = 0;
+}
+
 void oracle_reset(OBatch* B, const double* pos /*[E,N,2]*/, const double* angle /*[E,N]*/,
                   const double* targets /*[E,T,2] or NULL*/, const uint8_t* target_idx /*[N] or NULL*/,
                   const uint8_t* team /*[N] or NULL*/)
 {
     int N = B->p.n_agents, T = B->p.n_targets;
+    static const uint8_t zeros[O_MAX_BODIES] = {0};
     for (int ei = 0; ei < B->n_envs; ++ei) {
-        OEnv* e = &B->e[ei];
-        ow_clear(&e->w);
-        for (int i = 0; i < N; ++i) {
-            ow_add_body(&e->w, (float)pos[((size_t)ei * N + i) * 2], (float)pos[((size_t)ei * N + i) * 2 + 1],
-                        (float)angle[(size_t)ei * N + i]);
-            e->target_idx[i] = target_idx ? target_idx[i] : 0;
-            e->health[i] = B->p.init_health;
-            e->cd_atk[i] = 0.0;
-            e->cd_mov[i] = 0.0;
-            e->alive[i] = 1;
-            e->team[i] = team ? team[i] : 0;
-        }
-        for (int t = 0; t < T; ++t)
-            e->targets[t] = targets ? v2((float)targets[((size_t)ei * T + t) * 2], (float)targets[((size_t)ei * T + t) * 2 + 1])
-                                    : v2(0.0f, 0.0f);
-        e->time_passed = 0.0;
-        e->done = 0;
-        e->winner = -1;
-        e->step_count = 0;
+        if (!targets)
+            for (int t = 0; t < T; ++t) B->e[ei].targets[t] = v2(0.0f, 0.0f);
+        reset_env(B, ei, pos + (size_t)ei * N * 2, angle + (size_t)ei * N, targets ? targets + (size_t)ei * T * 2 : NULL,
+                  target_idx ? target_idx : zeros, team ? team : zeros);
     }
+}
+
+/* A new episode for ONE env of the batch (the reference's env.reset(), mvmnt.py:224-233 / combat.py:229-239,
+ * with the repaired semantics of SURVEY App. B3: a fresh world with newly drawn bodies); target indices and
+ * teams are kept. */
+void oracle_reset_env(OBatch* B, int ei, const double* pos /*[N,2]*/, const double* angle /*[N]*/,
+                      const double* targets /*[T,2] or NULL = keep*/)
+{
+    reset_env(B, ei, pos, angle, targets, NULL, NULL);
 }
 
 static inline double wrap_pi(double t)

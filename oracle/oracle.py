@@ -54,6 +54,7 @@ def lib():
         L.oracle_create.argtypes = [C.POINTER(OParams), C.c_int]
         L.oracle_destroy.argtypes = [vp]
         L.oracle_reset.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.oracle_reset_env.argtypes = [vp, C.c_int, vp, vp, vp]
         L.oracle_flock_step.argtypes = [vp] * 9 + [C.c_int]
         L.oracle_flock_observe.argtypes = [vp] * 4
         L.oracle_tdm_step.argtypes = [vp] * 8 + [C.c_int]
@@ -140,6 +141,14 @@ class OracleBatch:
         if team is not None:
             self.team = np.ascontiguousarray(team, np.uint8).reshape(self.N)
         lib().oracle_reset(self._h, _p(pos), _p(angle), _p(targets), _p(self.target_idx), _p(self.team))
+
+    def reset_env(self, ei, pos, angle, targets=None):
+        """A new episode for env `ei` alone (fresh world, new bodies; target indices and teams are kept)."""
+        pos = np.ascontiguousarray(pos, np.float64).reshape(self.N, 2)
+        angle = np.ascontiguousarray(angle, np.float64).reshape(self.N)
+        if targets is not None:
+            targets = np.ascontiguousarray(targets, np.float64).reshape(self.T, 2)
+        lib().oracle_reset_env(self._h, int(ei), _p(pos), _p(angle), _p(targets))
 
     def bodies(self):
         out = np.zeros((self.E, self.N, 10), np.float32)

@@ -160,3 +160,120 @@ def test_batches_on_their_own_streams():
     for a, b in zip(serial, par):
         for n in ("posvel", "angsleep", "fat", "obs", "nn_idx", "rewards", "contact_count"):
             assert torch.equal(a.state[n], b.state[n]), n
+
+
+def test_host_path_is_ordered_against_the_callers_stream():
+    """reset / step on the caller's stream followed by step_host (the handle's own stream) and back --
+    with the pinned buffers already allocated, so nothing synchronises by accident."""
+    import torch
+    import gym_macm
+    E, N = 4096, 16
+    a = gym_macm.BatchedFlock(E, n_agents=[N], device="cuda:0", seed=2)
+    b = gym_macm.BatchedFlock(E, n_agents=[N], device="cuda:0", seed=2)
+    b.engine.pinned()
+    torch.cuda.synchronize()
+    g = torch.Generator().manual_seed(0)
+    acts = torch.zeros((12, E, N, 4), dtype=torch.uint8)
+    acts[..., :3] = torch.randint(0, 3, (12, E, N, 3), generator=g, dtype=torch.uint8)
+    acts_d = acts.cuda()
+    hact = [x.pin_memory() for x in acts]
+    side = torch.cuda.Stream(device="cuda:0")
+    for rep in range(3):
+        a.reset(seed=40 + rep)
+        with torch.cuda.stream(side):        # b's device-side calls go to a stream of their own
+            b.reset(seed=40 + rep)           # sample + reset + observe kernels, still running when ...
+            for k in range(3):
+                b.step(acts_d[k])
+        for k in range(3):
+            a.step(acts_d[k])
+        for k in range(3, 6):                # ... the host path takes over
+            a.step(acts_d[k])
+            b.engine.step_host(hact[k], wait=False)
+        with torch.cuda.stream(side):
+            for k in range(6, 9):            # and back to the caller's stream without a host_sync in between
+                b.step(acts_d[k])
+        for k in range(6, 9):
+            a.step(acts_d[k])
+        torch.cuda.synchronize()
+        for n in ("posvel", "angsleep", "fat", "obs", "nn_idx", "rewards", "contact_count", "env_state"):
+            assert torch.equal(a.state[n], b.state[n]), (rep, n)
+
+
+def test_one_d2h_slab_and_pack_kernel():
+    import torch
+    import gym_macm
+    E, N = 64, 10
+    env = gym_macm.BatchedFlock(E, n_agents=[N], device="cuda:0", seed=1)
+    t, lay = env.engine.t, env.engine._out_layout
+    base = env.engine._out_slab.data_ptr()
+    order = sorted(lay, key=lambda n: lay[n][0])
+    assert order == ["obs", "rewards", "done", "nn_idx", "collided"]
+    for n in order:      # the five outputs lie back to back in one device slab, 16-byte aligned
+        assert t[n].data_ptr() == base + lay[n][0] and lay[n][0] % 16 == 0
+    p = env.engine.pinned()
+    assert all(p[n].data_ptr() - p["_slab"].data_ptr() == lay[n][0] for n in order)
+    # any integer dtype / width-3 actions go through the library's own pack kernel
+    a64 = torch.randint(0, 3, (E, N, 3), device="cuda:0")
+    env.step(a64)
+    want = torch.zeros((E, N, 4), dtype=torch.uint8, device="cuda:0")
+    want[..., :3] = a64.to(torch.uint8)
+    assert torch.equal(env._act4, want)
+    env2 = gym_macm.BatchedFlock(E, n_agents=[N], device="cuda:0", seed=1)
+    env2.step(want)
+    env2.step_host(want.cpu())
+    env.step(a64.to(torch.int32))
+    torch.cuda.synchronize()
+    for n in ("posvel", "obs", "rewards"):
+        assert torch.equal(env.state[n], env2.state[n])
+    hp = env2.engine.pinned()
+    for n in order:
+        assert torch.equal(hp[n], env2.state[n].cpu()), n
+
+
+def test_overflow_is_reported():
+    """A pile denser than the contact capacity: the flags are sticky, counted on the device, visible as
+    `overflowed`, and step() raises with check_overflow=True."""
+    import torch
+    import gym_macm
+    from gym_macm import _lib
+    E, N = 8, 32
+    rng = np.random.default_rng(0)
+    pos = rng.uniform(-1.2, 1.2, (E, N, 2))
+    pos[4:] = rng.uniform(-40, 40, (E - 4, N, 2))                 # envs 4.. are sparse
+    ang = np.zeros((E, N))
+    act = torch.ones((E, N, 4), dtype=torch.uint8, device="cuda:0")
+    env = gym_macm.BatchedFlock(E, n_agents=[N], device="cuda:0", seed=None, max_contacts=40, max_touching=16)
+    env.load_state(pos, ang)
+    env.step(act)
+    assert env.overflowed[:4].all() and not env.overflowed[4:].any()
+    c, t = env.overflow_count()
+    assert c == 4 and t == 4
+    for _ in range(3):
+        env.step(act)
+    assert env.overflowed[:4].all()                                # sticky
+    dbg = gym_macm.BatchedFlock(E, n_agents=[N], device="cuda:0", seed=None, max_contacts=40, max_touching=16,
+                                check_overflow=True)
+    dbg.load_state(pos, ang)
+    with pytest.raises(_lib.MacmError, match="overflow"):
+        dbg.step(act)
+    ok = gym_macm.BatchedFlock(E, n_agents=[N], device="cuda:0", seed=3, check_overflow=True)
+    ok.step(act)
+    assert ok.overflow_count() == (0, 0)
+
+
+def test_render_state_of_one_env():
+    import gym_macm
+    env = gym_macm.BatchedFlock(16, n_agents=[5], targets=[0, 0, 1, 1, 1], device="cuda:0", seed=4, start_spread=2.0)
+    import torch
+    env.step(torch.ones((16, 5, 4), dtype=torch.uint8, device="cuda:0"))
+    fr = env.render_state(3)
+    pv = env.state["posvel"][3].cpu().numpy()
+    col = env.state["collided"][3].cpu().numpy()
+    assert len(fr.world.bodies) == 5 and set(fr.gui_objects) == {"target0", "target1"}
+    for i, b in enumerate(fr.world.bodies):
+        assert b.transform.position == (float(pv[i, 0]), float(pv[i, 1])) and b.fixtures[0].shape.radius == 0.5
+        assert tuple(b.userData.color) == ((1.0, 0.2, 0.2) if col[i] else (0.4, 0.4, 0.6))
+    assert col.any()     # 5 agents in a 2 m square touch
+    tdm = gym_macm.BatchedTDM(4, n_agents=[2, 2], device="cuda:0", seed=0)
+    fr = tdm.render_state(1)
+    assert [tuple(b.userData.color) for b in fr.world.bodies] == [(0.2, 0.2, 1.0)] * 2 + [(1.0, 0.2, 0.2)] * 2
