@@ -10,9 +10,15 @@ is one Flock.step for all 4096 envs = one kernel launch.  The footprint of one b
 fits in the 126 MB L2, so the timed loop rotates over ROT independent batches (> 2x L2 in
 total): every step's inputs come from HBM.
 
+The headline spreads the rotation's independent batches over two streams (a batch keeps its stream): one
+batch's last envs -- a few worlds with long contact islands -- finish while the next batch's blocks take over
+the SMs.  Short driver windows (--steps 20) are repeated and the per-rank median taken.
+
 N > 1 (torchrun, one rank per GPU): each rank owns its own 4096 envs (weak scaling); envs are
-independent, so the data path has no collective.  `--gather` adds the optional NCCL all-gather
-of obs+rewards to every rank (the learner-side exchange of BASELINE config 5).
+independent, so the data path has no collective.  Legs beside the headline: the same steps on one stream,
+an isolated launch, macm_rollout, BASELINE configs 3 / 4 / 5 (16M-agent point), and with N > 1 the
+learner-side exchange of config 5 both ways (step kernel storing into the learner's memory over NVLink,
+and an NCCL all-gather).
 """
 import argparse
 import json
@@ -144,7 +150,8 @@ def cpu_oracle_rate(n_envs, n_threads, budget_s, seed=1234):
     from oracle import oracle
     rng = np.random.default_rng(seed)
     pos, ang, tg = random_state(rng, n_envs, N_AGENTS, 1)
-    ref = oracle.OracleBatch(n_envs, n_agents=N_AGENTS, n_targets=1, reward_mode=1)
+    ref = oracle.OracleBatch(n_envs, n_agents=N_AGENTS, n_targets=1, reward_mode=1,
+                             damping_model=DAMPING_CODE[default_damping()])
     ref.reset(pos, ang, targets=tg)
     acts = rng.integers(0, 3, (8, n_envs, N_AGENTS, 3)).astype(np.int32)
     for k in range(2):
@@ -159,21 +166,36 @@ def cpu_oracle_rate(n_envs, n_threads, budget_s, seed=1234):
     return n_envs * N_AGENTS * steps / el, steps, el
 
 
+def pybox2d_probe(seconds=0.0):
+    """oracle/pybox2d_probe.py in a subprocess (clean sys.path): is a real Box2D importable, what do the
+    discriminators select, and -- with `seconds` -- how fast is the reference's own Flock.step loop."""
+    try:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "pybox2d_probe.py"), "--time", str(seconds)],
+                             capture_output=True, text=True, timeout=60 + 4 * seconds, env={**os.environ, "PYTHONPATH": ROOT})
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as ex:
+        return {"available": False, "why": "probe failed: %r" % (ex,)}
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path.  pybox2d cannot be
-    installed (no wheel, no network), so this is the oracle port on every host thread."""
+    """--impl reference: the reference's CPU implementation of the path.  The probe looks for a real pybox2d first
+    (kind "pybox2d": the reference's own Flock.step loop); without one -- this image has no wheel and no network --
+    it is the oracle port on every host thread (kind "port")."""
     if rank != 0:
         return
     import numpy as np
     from oracle import oracle
     oracle.build()
     cores = len(os.sched_getaffinity(0))
+    probe = pybox2d_probe(seconds=8.0)
+    real = probe.get("reference_loop") if probe.get("available") else None
     # a bounded sample of the 4096-env batch per step: 64 envs per host thread, so that starting and joining the
     # worker threads (once per step) stays below a tenth of the step
     sample_envs = min(N_ENVS, 64 * cores)
     rng = np.random.default_rng(1234)
     pos, ang, tg = random_state(rng, sample_envs, N_AGENTS, 1)
-    ref = oracle.OracleBatch(sample_envs, n_agents=N_AGENTS, n_targets=1, reward_mode=1)
+    ref = oracle.OracleBatch(sample_envs, n_agents=N_AGENTS, n_targets=1, reward_mode=1,
+                             damping_model=DAMPING_CODE[default_damping()])
     ref.reset(pos, ang, targets=tg)
     acts = rng.integers(0, 3, (16, sample_envs, N_AGENTS, 3)).astype(np.int32)
     for k in range(args.warmup):
@@ -185,15 +207,80 @@ def run_reference(args, rank, world):
     val = sample_envs * N_AGENTS * args.steps / el
     sample = "%d of the %d envs per step (x%d agents), %d steps, oracle port on %d threads" % (
         sample_envs, N_ENVS, N_AGENTS, args.steps, cores)
+    kind = "port"
+    if real and "agent_steps_per_sec" in real:
+        # the real thing: pybox2d + the reference's Python host, single process (it has no batch axis)
+        kind, val, cores = "pybox2d", float(real["agent_steps_per_sec"]), 1
+        sample = "the reference's Flock.step loop, 1 env x %d agents, %d steps in %.1f s, single process" % (
+            real["n_agents"], real["steps"], real["seconds"])
+        el = args.steps * N_ENVS * N_AGENTS / val
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample,
-                   "note": "pybox2d is not installable here; CPU restatement (oracle/), not pybox2d"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                   "note": "pybox2d is not installable here; CPU restatement (oracle/), not pybox2d" if kind == "port"
+                           else "pybox2d + the reference's Python host",
+                   "pybox2d_probe": {k: probe.get(k) for k in ("available", "why", "damping_model", "box2d_version") if k in probe}},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+DAMPING_CODE = {"taylor": 0, "pade": 1}
+
+
+def default_damping():
+    from gym_macm.settings import flockSettings
+    return flockSettings().damping_model
+
+
+class Timer(object):
+    """Device timing of step sequences: windows of exactly K steps, each bracketed by a barrier over the ranks and
+    a device synchronisation on both sides and timed with CUDA events on the stream the steps are enqueued from
+    (side streams fork after the start event and join before the stop event).  A rank's figure is the MEDIAN of
+    its windows; the job's figure is the MAX over the ranks."""
+
+    def __init__(self, torch, dist, dev, world):
+        self.torch, self.dist, self.dev, self.world = torch, dist, dev, world
+        self.main = torch.cuda.current_stream(dev)
+
+    def max_over_ranks(self, x):
+        if self.world > 1:
+            t = self.torch.tensor([x], device=self.dev, dtype=self.torch.float64)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    def windows(self, issue, K, n_windows, streams=(), k0=0, after=None):
+        torch = self.torch
+        ms, k = [], k0
+        for w in range(n_windows):
+            torch.cuda.synchronize()
+            if self.world > 1:
+                self.dist.barrier()
+                torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for st in streams:
+                st.wait_stream(self.main)      # every stream starts after the start event ...
+            for j in range(K):
+                issue(k)
+                k += 1
+            for st in streams:
+                self.main.wait_stream(st)      # ... and the stop event waits for all of them
+            if after is not None:
+                after()
+            e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        med = statistics.median(ms)
+        return self.max_over_ranks(med), ms, k
+
+
+def n_windows_for(K):
+    # short driver windows (K = 20 is 0.4 ms) are repeated and the median taken; long ones stand alone
+    return 1 if K >= 400 else max(3, min(25, 500 // max(K, 1)))
 
 
 def main():
@@ -206,12 +293,11 @@ def main():
     ap.add_argument("--envs", type=int, default=N_ENVS)
     ap.add_argument("--no-numa", action="store_true", help="do not bind the ranks to their GPU's NUMA node")
     ap.add_argument("--rollout", type=int, default=32, help="steps per launch of the macm_rollout leg (0 = skip it)")
-    ap.add_argument("--streams", type=int, default=1,
-                    help="streams the independent batches of the rotation are spread over (a batch keeps its stream)")
-    ap.add_argument("--gather", action="store_true", help="NCCL all-gather of obs+rewards every step")
-    ap.add_argument("--gather-peer", action="store_true",
-                    help="obs+rewards+done of every rank written into rank 0's buffers by the step kernel itself "
-                         "(gym_macm.dist.PeerGather: NVLink peer stores, no collective)")
+    ap.add_argument("--streams", type=int, default=2,
+                    help="streams the independent batches of the rotation are spread over (a batch keeps its stream); "
+                         "2 = a batch's last envs finish while the next batch starts")
+    ap.add_argument("--windows", type=int, default=0, help="timed windows of --steps steps (0 = 25 for short windows, 1 for long)")
+    ap.add_argument("--no-legs", action="store_true", help="headline + e2e only (no other configs, no exchange legs)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--e2e-steps", type=int, default=240)
     ap.add_argument("--e2e-depth", type=int, default=3, help="independent batches in flight on the host-buffer path")
@@ -255,7 +341,11 @@ def main():
             os.dup2(keep, 1)
             os.close(keep)
     E, N, ROT = args.envs, N_AGENTS, args.rot
+    K = args.steps
+    NW = args.windows if args.windows > 0 else n_windows_for(K)
     sampler = ClockSampler(local) if rank == 0 else None   # started early: it is warm when the timed region begins
+    T = Timer(torch, dist, dev, world)
+    main_stream = T.main
 
     extra = {"max_touching": args.max_touching} if args.max_touching else {}
     sims = [gym_macm.BatchedFlock(E, n_agents=[N], reward_mode="linear", device=dev, seed=1234 + 1000 * rank + r, **extra)
@@ -266,129 +356,78 @@ def main():
     POOL = 61   # prime: batch r at its j-th step uses action set (j + 7 r) mod POOL, all distinct in sequence
     acts = torch.zeros((POOL, E, N, 4), dtype=torch.uint8, device=dev)
     acts[..., :3] = torch.randint(0, 3, (POOL, E, N, 3), generator=g, device=dev, dtype=torch.uint8)
-    gathered, gstream = None, None
-    if args.gather and world > 1:
-        # learner-side exchange of BASELINE config 5: every rank receives every shard's obs + rewards.
-        # It runs on a side stream: the next batch steps while this batch's outputs cross NVLink.
-        gathered = [torch.empty((world,) + tuple(sims[0].state[k].shape), dtype=sims[0].state[k].dtype, device=dev)
-                    for k in ("obs", "rewards")]
-        gstream = torch.cuda.Stream(device=dev)
 
-    main_stream = torch.cuda.current_stream(dev)
     NS = max(1, min(args.streams, ROT))
-    streams = [torch.cuda.Stream(device=dev) for _ in range(NS)] if NS > 1 else [None]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(NS)] if NS > 1 else []
 
-    peer = None
-    if args.gather_peer and world > 1:
-        from gym_macm.dist import PeerGather
-        peer = [PeerGather(s_, world * E, learner=0, names=("obs", "rewards", "done")) for s_ in sims[:1]]
-        peer_out = peer[0].mine   # every batch of the rotation writes into the same two buffer sets on the learner
+    def act_of(k):
+        return acts[(k // ROT + 7 * (k % ROT)) % POOL]
 
-    def one_step(k):
-        s = sims[k % ROT]
-        st = streams[(k % ROT) % NS]
-        if peer is not None:
-            s.engine.rollout(acts[(k // ROT + 7 * (k % ROT)) % POOL], 1, None, 0, peer_out[k & 1], st)
-            return
-        if args.policy == "flock":
-            with torch.cuda.stream(st if st is not None else main_stream):
-                a = s.bot_actions("flock")
-        else:
-            a = acts[(k // ROT + 7 * (k % ROT)) % POOL]
-        s.engine.step(a, st)
-        if gathered is not None:
-            gstream.wait_stream(st if st is not None else main_stream)
-            with torch.cuda.stream(gstream):
-                dist.all_gather_into_tensor(gathered[0], s.state["obs"])
-                dist.all_gather_into_tensor(gathered[1], s.state["rewards"])
+    def step_on(strs):
+        def issue(k):
+            s = sims[k % ROT]
+            st = strs[(k % ROT) % len(strs)] if strs else None
+            if args.policy == "flock":
+                with torch.cuda.stream(st if st is not None else main_stream):
+                    a = s.bot_actions("flock")
+            else:
+                a = act_of(k)
+            s.engine.step(a, st)
+        return issue
 
     # settle: every batch runs SETTLE steps (1.07 s of simulated time of a 60 s / 3601-step episode)
     # so that the overlaps of the random spawn are resolved; then W warm-up steps of the rotation
+    issue, issue1 = step_on(streams), step_on([])
     for k in range(args.settle * ROT):
-        one_step(k)
+        issue1(k)
+    torch.cuda.synchronize()
+    for st in streams:
+        st.wait_stream(main_stream)
     for k in range(args.warmup):
-        one_step(k)
+        issue(k)
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     launches0 = sum(s.engine.launch_count for s in sims)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
     t0 = time.time()
-    ev0.record()
-    for st in streams:
-        if st is not None:
-            st.wait_stream(main_stream)      # every stream starts after the start event ...
-    for k in range(args.steps):
-        one_step(k)
-    for st in streams:
-        if st is not None:
-            main_stream.wait_stream(st)      # ... and the stop event waits for all of them
-    if gstream is not None:
-        torch.cuda.current_stream(dev).wait_stream(gstream)   # the last gathers are part of the timed region
-    ev1.record()
-    torch.cuda.synchronize()
+    ms_win, ms_all, knext = T.windows(issue, K, NW, streams)
     t1 = time.time()
-    ms = ev0.elapsed_time(ev1)
     launches = sum(s.engine.launch_count for s in sims) - launches0
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        dist.barrier()
     clocks = sampler.stop(t0, t1) if sampler else None
-    ms_per_step = ms / args.steps
-    value = world * E * N * args.steps / (ms * 1e-3)
+    ms_per_step = ms_win / K
+    value = world * E * N / (ms_per_step * 1e-3)
 
-    def max_over_ranks(x):
-        if world > 1:
-            t = torch.tensor([x], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-        return x
-
-    # ---- two further legs, reported beside the headline (same workload, same batches, device-timed) -----
-    # (1) the independent batches of the rotation spread over two streams: one batch's tail (a few envs with
-    #     long islands finishing alone) overlaps the next batch's body.  What a rollout worker with several
-    #     env batches in flight gets.
     legs = {}
-    if NS == 1 and ROT >= 2 and gathered is None and peer is None and args.policy == "random":
-        st2 = [torch.cuda.Stream(device=dev) for _ in range(2)]
-        for rep_ in range(2):      # first pass = warm-up
+    plain = args.policy == "random" and not args.no_legs
+    # ---- further device-timed legs on the same batches ------------------------------------------------------
+    # (1) everything on ONE stream: every launch waits for the last env of the one before it (the r1 headline)
+    if plain and NS > 1:
+        T.windows(issue1, min(K, 200), 1)     # warm-up of this shape
+        ms1, all1, _ = T.windows(issue1, K, NW)
+        legs["one_stream"] = {"value": world * E * N * K / (ms1 * 1e-3), "unit": UNIT, "ms_per_step": ms1 / K,
+                               "windows": NW, "note": "the same steps on one stream: no overlap between a batch's "
+                               "tail (a few envs with long contact islands) and the next batch"}
+    # (2) one launch alone on an idle GPU (synchronised on both sides): the kernel's own duration
+    iso = []
+    if plain:
+        for k in range(40):
             torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
-            for st in st2:
-                st.wait_stream(main_stream)
-            for k in range(args.steps):
-                sims[k % ROT].engine.step(acts[(k // ROT + 7 * (k % ROT)) % POOL], st2[(k % ROT) & 1])
-            for st in st2:
-                main_stream.wait_stream(st)
-            a1.record()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            sims[k % ROT].engine.step(act_of(knext + k))
+            e1.record()
             torch.cuda.synchronize()
-        ms2 = max_over_ranks(a0.elapsed_time(a1))
-        legs["two_streams"] = {"value": world * E * N * args.steps / (ms2 * 1e-3), "unit": UNIT,
-                                "ms_per_step": ms2 / args.steps, "steps": args.steps,
-                                "note": "same steps, the rotation's batches alternating between two streams"}
-    # (2) macm_rollout: R steps of a batch per launch, the envs' bodies held on chip between the steps; every
+            iso.append(e0.elapsed_time(e1))
+        iso = T.max_over_ranks(statistics.median(iso[8:]))
+    # (3) macm_rollout: R steps of a batch per launch, the envs' bodies held on chip between the steps; every
     #     step still writes its obs / nn_idx / rewards / collided / done (to per-step arrays).
-    if gathered is None and peer is None and args.policy == "random" and args.rollout > 0:
+    if plain and args.rollout > 0:
         R = min(args.rollout, POOL)
         outs = [sims[0].engine.rollout_buffers(R) for _ in range(2)]
-        n_launch = max(ROT, (args.steps // R) // ROT * ROT)
-        for rep_ in range(2):
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
-            for j in range(n_launch):
-                sims[j % ROT].engine.rollout(acts[:R], R, None, 0, outs[j & 1])
-            a1.record()
-            torch.cuda.synchronize()
-        msr = max_over_ranks(a0.elapsed_time(a1))
+        n_launch = max(ROT, (min(K * NW, 2000) // R) // ROT * ROT)
+
+        def roll(j):
+            sims[j % ROT].engine.rollout(acts[:R], R, None, 0, outs[j & 1])
+        T.windows(roll, ROT, 1)
+        msr, _, _ = T.windows(roll, n_launch, 1)
         legs["rollout"] = {"value": world * E * N * n_launch * R / (msr * 1e-3), "unit": UNIT,
                             "ms_per_step": msr / (n_launch * R), "steps_per_launch": R, "launches": n_launch,
                             "note": "macm_rollout, per-step outputs written every step; bit-identical to single steps "
@@ -398,18 +437,63 @@ def main():
     # live contacts per agent (c-bar of the roofline formula), measured on this rank's batches
     c_bar = float(sum(float(s.state["contact_count"].sum()) for s in sims) / (ROT * E * N))
     touching = float(sum(float(s.state["env_state"][:, 2].sum()) for s in sims) / (ROT * E))
+    overflow = [sum(x) for x in zip(*[s.overflow_count() for s in sims])]
     b_alg = b_alg_per_agent_step(c_bar, 1, N)
     peak, peak_kind = measured_peak()
     achieved = b_alg * E * N / (ms_per_step * 1e-3) / 1e9   # GB/s of ONE GPU's kernel
-    traffic = None
+    static = {}
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            static = json.load(f)
     except Exception:
         pass
 
+    # ---- the exchange BASELINE config 5 names: obs + rewards (+ done) of every shard to a learner rank ------
+    if world > 1 and plain:
+        from gym_macm.dist import PeerGather
+        nbytes_in = (world - 1) * E * N * (16 + 4) + (world - 1) * E   # into the learner per step
+        # (a) the step kernel stores its outputs into rank 0's buffers itself (NVLink peer stores, no collective)
+        peer = PeerGather(sims[0], world * E, learner=0, names=("obs", "rewards", "done"))
+
+        def peer_step(k):
+            s = sims[k % ROT]
+            st = streams[(k % ROT) % NS] if streams else None
+            s.engine.rollout(act_of(k), 1, None, 0, peer.mine[k & 1], st)
+        T.windows(peer_step, min(K, 100), 1, streams)
+        msp, _, _ = T.windows(peer_step, K, NW, streams)
+        legs["gather_peer"] = {"value": world * E * N * K / (msp * 1e-3), "unit": UNIT, "ms_per_step": msp / K,
+                                "bytes_into_learner_per_step": nbytes_in,
+                                "learner_ingress_GBps": nbytes_in / (msp / K * 1e-3) / 1e9, "windows": NW,
+                                "note": "obs+rewards+done of every rank stored into rank 0's buffers by the step kernel "
+                                        "itself (gym_macm.dist.PeerGather: NVLink peer stores through CUDA IPC, no collective)"}
+        # (b) NCCL all-gather of obs + rewards on a side stream: the next batch steps while this one's outputs travel
+        gathered = [torch.empty((world,) + tuple(sims[0].state[k_].shape), dtype=sims[0].state[k_].dtype, device=dev)
+                    for k_ in ("obs", "rewards")]
+        gstream = torch.cuda.Stream(device=dev)
+
+        def nccl_step(k):
+            s = sims[k % ROT]
+            s.engine.step(act_of(k))
+            gstream.wait_stream(main_stream)
+            with torch.cuda.stream(gstream):
+                dist.all_gather_into_tensor(gathered[0], s.state["obs"])
+                dist.all_gather_into_tensor(gathered[1], s.state["rewards"])
+
+        def join():
+            main_stream.wait_stream(gstream)
+        T.windows(nccl_step, min(K, 50), 1, after=join)
+        msn, _, _ = T.windows(nccl_step, K, max(3, NW // 3), after=join)
+        legs["gather_nccl"] = {"value": world * E * N * K / (msn * 1e-3), "unit": UNIT, "ms_per_step": msn / K,
+                                "bytes_into_every_rank_per_step": (world - 1) * E * N * 20,
+                                "ingress_GBps": (world - 1) * E * N * 20 / (msn / K * 1e-3) / 1e9,
+                                "note": "NCCL all_gather_into_tensor of obs and rewards to every rank, on a side stream"}
+        del gathered, peer
+
+    # ---- the other BASELINE configs, each rotated over more than 2x L2 ----------------------------------------
+    if plain:
+        legs["configs"] = other_configs(torch, gym_macm, T, dev, world, rank, K, NW, peak, args.settle)
+
     # ---- end to end through the host-buffer entry point (macm_step_host) --------------------
-    e2e = None
     # DEPTH batches in rotation (the usual double/triple-buffered rollout): while one batch's
     # observations travel to the host, the others step.  Every step still pays its own H2D of actions
     # (from pinned host memory, where the host policy left them) and its own D2H of obs + rewards +
@@ -436,16 +520,14 @@ def main():
     for s_ in pp:
         s_.engine.host_sync()
     el = time.perf_counter() - te
-    if world > 1:
-        t = torch.tensor([el], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        el = float(t.item())
+    el = T.max_over_ranks(el)
     h2d = int(host_actions[0].numel() * host_actions[0].element_size())
-    d2h = int(sum(pin[k].numel() * pin[k].element_size() for k in ("obs", "rewards", "done")))
+    d2h = int(sum(pin[k].numel() * pin[k].element_size() for k in want))
     e2e = {"value": world * E * N * args.e2e_steps / el, "unit": UNIT, "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
+           "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "d2h_transfers_per_step": 1,
+           "pcie_GBps_per_gpu": (h2d + d2h) * args.e2e_steps / el / 1e9,
            "path": "macm_step_host_async/macm_host_sync on %d batches in rotation: pinned host actions -> device, "
-                   "step kernel, obs+rewards+done -> pinned host" % DEPTH}
+                   "step kernel, obs+rewards+done -> pinned host in ONE transfer (output slab)" % DEPTH}
 
     if rank == 0:
         cpu = None
@@ -462,37 +544,161 @@ def main():
                                  % (n_envs, N, st, el),
                        "single_thread": {"value": rate1, "unit": UNIT, "cores": 1,
                                          "sample": "8 envs x %d agents x %d steps in %.1f s" % (N, st1, el1)}}
+                probe = pybox2d_probe(seconds=3.0)
+                cpu["pybox2d_probe"] = probe
+                real = probe.get("reference_loop") if probe.get("available") else None
+                if real and "agent_steps_per_sec" in real:
+                    cpu["pybox2d"] = {"value": real["agent_steps_per_sec"], "unit": UNIT, "cores": 1, "kind": "pybox2d",
+                                      "sample": "the reference's Flock.step loop, %d steps in %.1f s" % (real["steps"], real["seconds"])}
             except Exception as ex:  # the checker missing must not hide the GPU number
                 cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
         info = sims[0].engine.info
+        kname = "macm_step_kernel<%d,%d,0,0>" % (info.lanes_per_env, info.agents_per_lane)
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": static.get("dram_bytes_per_launch"),
+                    "traffic_kind": "static: %s" % static.get("source", "profiles/traffic.json"),
+                    "peak_kind": peak_kind, "bytes_per_agent_step": b_alg, "kernel": kname,
+                    "kernel_ms": ms_per_step,
+                    "kernel_ms_kind": "launch-to-launch interval of the timed region (consecutive launches overlap: "
+                                      "programmatic dependent launch, %d streams)" % NS}
+        if iso:
+            roofline["kernel_ms_isolated"] = iso
+            roofline["frac_isolated"] = b_alg * E * N / (iso * 1e-3) / 1e9 / peak
+        # what actually bounds the kernel (profiles/README.md): warp-instruction issue.  The instruction count is
+        # the ncu figure of the committed capture; the peak is one instruction per clock on each of the SMs' four
+        # sub-partitions.
+        inst = static.get("warp_inst_per_env_step")
+        roofline_issue = None
+        if inst:
+            sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
+            nsp = info.sm_count * 4
+            floor_ms = inst * E / (nsp * sm_clock * 1e6) * 1e3
+            roofline_issue = {"bound": "issue", "warp_inst_per_env_step": inst, "inst_kind": "static: %s" % static.get("source"),
+                              "sub_partitions": nsp, "sm_mhz": sm_clock, "floor_ms": floor_ms,
+                              "achieved": inst * E / (ms_per_step * 1e-3) / 1e12, "peak": nsp * sm_clock * 1e6 / 1e12,
+                              "unit": "T warp-inst/s", "frac": floor_ms / ms_per_step}
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "windows": NW, "window_ms": ms_all,
+            "window_agg": "each window = %d steps between barrier+synchronize; per-rank median of %d windows, max over ranks" % (K, NW),
             "config": {"workload": WORKLOAD, "envs_per_gpu": E, "agents_per_env": N, "reward_mode": "linear",
                        "actions": "pre-generated on device, U{0,1,2}^3" if args.policy == "random" else "bots.flock on device",
                        "l2": "inputs larger than L2: rotation over %d independent batches (%.0f MB of state+outputs)"
                              % (ROT, ROT * E * N * 73 / 1e6),
                        "streams": NS, "numa_bound_cpus": len(numa_cpus) if numa_cpus else None,
-                       "parallelism": "envs sharded, %d per GPU, no data-path collective%s" % (
-                           E, " + NCCL all-gather of obs/rewards" if gathered is not None else (
-                               " + obs/rewards/done stored into rank 0's buffers by the step kernel (NVLink peer stores)"
-                               if peer is not None else "")),
+                       "damping_model": default_damping(),
+                       "parallelism": "envs sharded, %d per GPU, no data-path collective" % E,
                        "launch": {"lanes_per_env": info.lanes_per_env, "agents_per_lane": info.agents_per_lane,
                                   "threads_per_block": info.threads_per_block, "blocks": info.blocks,
                                   "smem_per_block": info.smem_bytes_per_block, "blocks_per_sm": info.blocks_per_sm},
                        "settle_steps_per_batch": args.settle,
-                       "contacts_per_agent": c_bar, "touching_contacts_per_env": touching},
+                       "contacts_per_agent": c_bar, "touching_contacts_per_env": touching,
+                       "envs_with_contact_overflow": overflow},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_kind": peak_kind, "bytes_per_agent_step": b_alg,
-                         "kernel": "macm_flock_step_kernel<32,2>", "kernel_ms": ms_per_step},
+            "roofline": roofline, "roofline_issue": roofline_issue,
             "cpu_baseline": cpu,
         }
         out.update(legs)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_configs(torch, gym_macm, T, dev, world, rank, K, NW, peak, settle):
+    """BASELINE configs 3, 4 and the 16M-agent point of config 5: device-timed like the headline (independent
+    batches alternating between two streams, footprint of the rotation > 2x the 126 MB L2), each with its own
+    algorithmic bytes per agent-step and roofline fraction."""
+    out = {}
+    g = torch.Generator(device=dev)
+    g.manual_seed(7 + rank)
+    st2 = [torch.cuda.Stream(device=dev) for _ in range(2)]
+
+    def run(name, sims, acts, n_agents, b_alg_fn, steps, workload):
+        ROT, POOL = len(sims), acts.shape[0]
+        E = sims[0].engine.E
+
+        def issue(k):
+            sims[k % ROT].engine.step(acts[(k // ROT + 3 * (k % ROT)) % POOL], st2[(k % ROT) & 1])
+        for k in range(settle * ROT):
+            sims[k % ROT].engine.step(acts[(k // ROT + 3 * (k % ROT)) % POOL])
+        torch.cuda.synchronize()
+        T.windows(issue, min(steps, 4 * ROT), 1, st2)
+        ms, _, _ = T.windows(issue, steps, NW, st2)
+        c_bar = float(sum(float(s.state["contact_count"].sum()) for s in sims) / (ROT * E * n_agents))
+        b = b_alg_fn(c_bar)
+        per = ms / steps
+        ach = b * E * n_agents / (per * 1e-3) / 1e9
+        foot = sum(sum(t.numel() * t.element_size() for t in s.state.values()) for s in sims)
+        ov = [sum(x) for x in zip(*[s.overflow_count() for s in sims])]
+        out[name] = {"workload": workload, "value": world * E * n_agents / (per * 1e-3), "unit": UNIT,
+                     "ms_per_step": per, "steps": steps, "windows": NW, "envs_per_gpu": E, "agents_per_env": n_agents,
+                     "batches_in_rotation": ROT, "footprint_MB": foot / 1e6, "contacts_per_agent": c_bar,
+                     "bytes_per_agent_step": b, "envs_with_contact_overflow": ov,
+                     "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}}
+
+    # config 3: multi-flock, 6 agents, targets=[0,0,1,1,2,2], 65,536 envs, binary reward
+    E3, N3 = 65536, 6
+    sims = [gym_macm.BatchedFlock(E3, n_agents=[N3], targets=[0, 0, 1, 1, 2, 2], device=dev, seed=31 + 100 * rank + r)
+            for r in range(10)]
+    acts = torch.zeros((7, E3, N3, 4), dtype=torch.uint8, device=dev)
+    acts[..., :3] = torch.randint(0, 3, (7, E3, N3, 3), generator=g, device=dev, dtype=torch.uint8)
+    run("config3_multi_flock", sims, acts, N3, lambda c: b_alg_per_agent_step(c, 3, N3), K,
+        "cm-flock-v0 6 agents, targets=[0,0,1,1,2,2], x 65536 envs per GPU, binary reward")
+    del sims, acts
+    # config 4: team deathmatch, 3 teams x 15 agents, 16,384 envs
+    E4, N4 = 16384, 45
+    sims = [gym_macm.BatchedTDM(E4, n_agents=[15, 15, 15], device=dev, seed=41 + 100 * rank + r) for r in range(2)]
+    acts = torch.randint(0, 3, (5, E4, N4, 4), generator=g, device=dev, dtype=torch.uint8)
+    acts[..., 3] = torch.randint(0, 2, (5, E4, N4), generator=g, device=dev, dtype=torch.uint8)
+    run("config4_tdm", sims, acts, N4, lambda c: 828.0 + 32.0 * c, max(4, min(K, 100)),
+        "cm-tdm-v0 3 teams x 15 agents x 16384 envs per GPU, random actions with attacks")
+    del sims, acts
+    # config 5: 64-agent flock envs, 32,768 per GPU (16.8M agents on 8 GPUs), no exchange here (see gather_* legs)
+    E5, N5 = 32768, N_AGENTS
+    sims = [gym_macm.BatchedFlock(E5, n_agents=[N5], reward_mode="linear", device=dev, seed=51 + 100 * rank + r)
+            for r in range(2)]
+    acts = torch.zeros((3, E5, N5, 4), dtype=torch.uint8, device=dev)
+    acts[..., :3] = torch.randint(0, 3, (3, E5, N5, 3), generator=g, device=dev, dtype=torch.uint8)
+    run("config5_32768_envs_per_gpu", sims, acts, N5, lambda c: b_alg_per_agent_step(c, 1, N5), max(4, min(K, 100)),
+        "cm-flock-v0 64 agents x 32768 envs per GPU (%.1fM agents on %d GPUs), linear reward" % (world * E5 * N5 / 1e6, world))
+    if world > 1:
+        import torch.distributed as dist
+        from gym_macm.dist import PeerGather
+        steps = max(4, min(K, 40))
+        peer = PeerGather(sims[0], world * E5, learner=0, names=("obs", "rewards", "done"))
+
+        def peer_step(k):
+            sims[k % 2].engine.rollout(acts[k % 3], 1, None, 0, peer.mine[k & 1], st2[k & 1])
+        T.windows(peer_step, 4, 1, st2)
+        msp, _, _ = T.windows(peer_step, steps, max(3, NW // 3), st2)
+        nb = (world - 1) * (E5 * N5 * 20 + E5)
+        out["config5_32768_envs_per_gpu"]["gather_peer"] = {
+            "value": world * E5 * N5 * steps / (msp * 1e-3), "unit": UNIT, "ms_per_step": msp / steps,
+            "bytes_into_learner_per_step": nb, "learner_ingress_GBps": nb / (msp / steps * 1e-3) / 1e9}
+        gathered = [torch.empty((world,) + tuple(sims[0].state[k_].shape), dtype=sims[0].state[k_].dtype, device=dev)
+                    for k_ in ("obs", "rewards")]
+        gstream = torch.cuda.Stream(device=dev)
+
+        def nccl_step(k):
+            s = sims[k % 2]
+            s.engine.step(acts[k % 3])
+            gstream.wait_stream(T.main)
+            with torch.cuda.stream(gstream):
+                dist.all_gather_into_tensor(gathered[0], s.state["obs"])
+                dist.all_gather_into_tensor(gathered[1], s.state["rewards"])
+
+        def join():
+            T.main.wait_stream(gstream)
+        T.windows(nccl_step, 4, 1, after=join)
+        msn, _, _ = T.windows(nccl_step, steps, 3, after=join)
+        out["config5_32768_envs_per_gpu"]["gather_nccl"] = {
+            "value": world * E5 * N5 * steps / (msn * 1e-3), "unit": UNIT, "ms_per_step": msn / steps,
+            "bytes_into_every_rank_per_step": (world - 1) * E5 * N5 * 20,
+            "ingress_GBps": (world - 1) * E5 * N5 * 20 / (msn / steps * 1e-3) / 1e9}
+        del gathered, peer
+    return out
 
 
 if __name__ == "__main__":

@@ -198,11 +198,16 @@ class PeerGather(object):
         """One step of this rank's shard; its outputs land in buffer set `self.k % n_buffers` on the learner."""
         out = self.mine[self.k % len(self.mine)]
         self.env.engine.rollout(actions, 1, None, 0, out, stream)
+        self._last_stream = stream if stream is not None else self.env.engine.stream
         self.k += 1
         return out
 
+    _last_stream = None
+
     def fence(self):
-        torch.cuda.current_stream(self.env.engine.device).synchronize()
+        """The stream the last step() ran on has finished on every rank (the learner may read the filled set)."""
+        st = self._last_stream if self._last_stream is not None else torch.cuda.current_stream(self.env.engine.device)
+        st.synchronize()
         dist.barrier(group=self.group)
 
     def gathered(self, back=1):
