@@ -499,9 +499,9 @@ def main():
     # (from pinned host memory, where the host policy left them) and its own D2H of obs + rewards +
     # done inside the timed region, and the host reads a result before it issues the batch's next step.
     DEPTH = max(1, min(args.e2e_depth, ROT))
-    pp = sims[:DEPTH]
+    pp = sims[:DEPTH] if args.e2e_steps > 0 else []
     want = ("obs", "rewards", "done")
-    pin = pp[0].engine.pinned()
+    pin = pp[0].engine.pinned() if pp else {}
     host_actions = [acts[i].cpu().pin_memory() for i in range(4)]
     for s_ in pp:
         for k in range(3):
@@ -522,8 +522,8 @@ def main():
     el = time.perf_counter() - te
     el = T.max_over_ranks(el)
     h2d = int(host_actions[0].numel() * host_actions[0].element_size())
-    d2h = int(sum(pin[k].numel() * pin[k].element_size() for k in want))
-    e2e = {"value": world * E * N * args.e2e_steps / el, "unit": UNIT, "h2d_bytes_per_step": h2d,
+    d2h = int(sum(pin[k].numel() * pin[k].element_size() for k in want)) if pp else 0
+    e2e = None if not pp else {"value": world * E * N * args.e2e_steps / el, "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "d2h_transfers_per_step": 1,
            "pcie_GBps_per_gpu": (h2d + d2h) * args.e2e_steps / el / 1e9,
            "path": "macm_step_host_async/macm_host_sync on %d batches in rotation: pinned host actions -> device, "

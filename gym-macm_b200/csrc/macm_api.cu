@@ -137,7 +137,7 @@ extern "C" int macm_params_default(macm_params* p, int env_kind)
     p->velocity_iterations = 8;
     p->position_iterations = 3;
     p->warm_starting = 1;
-    p->damping_model = MACM_DAMPING_TAYLOR;
+    p->damping_model = MACM_DAMPING_PADE;   // pip pybox2d bundles Box2D >= 2.3.1 (see gym_macm/settings.py)
     p->radius = 0.5;
     p->density = 1.0;
     p->friction = 0.3;
@@ -374,6 +374,10 @@ extern "C" int macm_bind(macm_sim* sim, const macm_buffers* b)
     K.env_state = (int4*)b->env_state; K.targets = (const float2*)b->targets; K.target_idx = b->target_idx;
     K.tdm = (float4*)b->tdm_state; K.team = b->team;
     K.obs = b->obs; K.nn_idx = b->nn_idx; K.rewards = b->rewards; K.collided = b->collided; K.done = b->done;
+    K.bulk = flock && K.action_mode == MACM_ACTION_DISCRETE && sim->cfg.G == 32 && (K.N & 3) == 0 && K.C >= 32 &&
+             28 * K.N + 384 <= 24 * K.TC && aligned(b->angsleep, 16) && aligned(b->contact_ab, 16) &&
+             aligned(b->contact_imp, 16) && ((K.C * 4) & 15) == 0;
+    if (getenv("MACM_NO_BULK")) K.bulk = 0;   // experiments
     sim->bound = 1;
     return MACM_OK;
 }

@@ -172,6 +172,35 @@ __device__ __forceinline__ void prefetch_l2(int gl, const void* p, int bytes)
         asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)p + off));
 }
 
+// 1-D bulk asynchronous copies global -> shared memory, completion counted in bytes on an mbarrier (TMA unit, no
+// tensor map): the step kernel fetches an env's contiguous state rows with a handful of instructions on one lane.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, int bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, int bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, int parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+
 // b2TestOverlap(b2AABB, b2AABB): d1 = b.lo - a.hi, d2 = a.lo - b.hi; overlap iff no component > 0.
 // With IEEE gradual underflow (no -ftz) x - y > 0 <=> x > y, so the subtractions are not needed.
 __device__ __forceinline__ bool aabb_overlap(const float4 a, const float4 b)
@@ -975,7 +1004,10 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
     // latency of the state off the critical path whenever there is a predecessor to overlap with.
     {
         // one line per lane: 8 lanes on posvel, 8 on the fat AABBs (or the TDM state after the first 4), 4 on
-        // angle/sleep, 2 on the actions, 1 + 2 on the head of the contact list, then the per-env scalars
+        // angle/sleep, 2 on the actions, 1 + 2 on the head of the contact list, then the per-env scalars.
+        // (Everything before griddepcontrol.wait runs while the predecessor drains: a branch-free / table-driven
+        // version of this ladder, 25 instead of 120 instructions, measured SLOWER -- 20.8 against 18.8 us per step --
+        // because its indexed constant loads delayed the prefetches; profiles/README.md, r2 finding 2.)
         const int env_ = slot, l = g.gl;
         const size_t a0 = (size_t)env_ * P.N;
         const int abytes = (TDM || P.action_mode == MACM_ACTION_DISCRETE) ? 4 : 8;
@@ -998,6 +1030,14 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
             prefetch_l2<G>(g.gl, P.angsleep + a0, P.N * 8);
         }
     }
+#ifdef MACM_BULK_STAGE
+    if (!TDM && G == 32 && P.bulk && g.gl == 0) {   // the two mbarriers of the bulk state copies (phase 0)
+        mbar_init(smem_u32(S.misc()), 1);
+        mbar_init(smem_u32(S.misc()) + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+#endif
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (P.trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_t0)); tr_c0 = clock64(); }
@@ -1017,7 +1057,30 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
     // first chunk of the contact list, fetched together with the state (one HBM round trip less)
     uint32_t pre_ab = 0u;
     float2 pre_imp = make_float2(0.0f, 0.0f);
-    if (g.gl < P.C) { pre_ab = c_ab[g.gl]; pre_imp = c_imp[g.gl]; }
+    // Bulk path (P.bulk, macm_sim.h): lane 0 issues six cp.async.bulk copies -- angle/sleep + actions on one
+    // mbarrier (all phase 1 needs), positions/velocities + fat AABBs + the head of the contact list on a second one
+    // that is only waited for after the float64 action decode -- into the still idle touching-contact stage (the
+    // fat AABBs land where they live).  Otherwise every lane loads its own agents' rows.
+#ifdef MACM_BULK_STAGE   // measured (profiles/README.md, r2 finding 3): no faster than per-lane loads; an experiment build
+    const bool bulk = !TDM && G == 32 && P.bulk && actions != nullptr && (reinterpret_cast<uintptr_t>(actions) & 15) == 0;
+#else
+    constexpr bool bulk = false;
+#endif
+    unsigned char* stg = S.base + Lay<NC>::FIXED;
+    const uint32_t bar = smem_u32(S.misc());
+    if (bulk) {
+        if (g.gl == 0) {
+            const size_t a0 = (size_t)env * N;
+            mbar_expect_tx(bar, N * 12);
+            bulk_g2s(smem_u32(stg + N * 16), P.angsleep + a0, N * 8, bar);
+            bulk_g2s(smem_u32(stg + N * 24), reinterpret_cast<const uint32_t*>(actions) + a0, N * 4, bar);
+            mbar_expect_tx(bar + 8, N * 32 + 384);
+            bulk_g2s(smem_u32(stg), P.posvel + a0, N * 16, bar + 8);
+            bulk_g2s(smem_u32(fat), P.fat + a0, N * 16, bar + 8);
+            bulk_g2s(smem_u32(stg + N * 28), c_ab, 128, bar + 8);
+            bulk_g2s(smem_u32(stg + N * 28 + 128), c_imp, 256, bar + 8);
+        }
+    } else if (g.gl < P.C) { pre_ab = c_ab[g.gl]; pre_imp = c_imp[g.gl]; }
     // TDM per-agent host state (combat.Agent): health, cool-downs (steps left), alive, hits taken
     float health[APL];
     int cd_atk[APL], cd_mov[APL], hits[APL];
@@ -1030,10 +1093,12 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
         valid[s] = i < N;
         team[s] = (TDM && valid[s]) ? P.team[i] : 0;
         const size_t gi = (size_t)env * N + (valid[s] ? i : 0);
-        const float4 pv = P.posvel[gi];
-        const float2 as = P.angsleep[gi];
-        fatr[s] = P.fat[gi];
-        c[s] = make_float2(pv.x, pv.y); v[s] = make_float2(pv.z, pv.w); ang[s] = as.x; slp[s] = as.y;
+        if (!bulk) {
+            const float4 pv = P.posvel[gi];
+            const float2 as = P.angsleep[gi];
+            fatr[s] = P.fat[gi];
+            c[s] = make_float2(pv.x, pv.y); v[s] = make_float2(pv.z, pv.w); ang[s] = as.x; slp[s] = as.y;
+        }
         was_alive[s] = valid[s];
         if (TDM) {
             const float4 td = P.tdm[gi];
@@ -1053,6 +1118,14 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
         if (!TDM && R.policy() == MACM_BOT_FLOCK && valid[s]) {
             const float4 o4 = reinterpret_cast<const float4*>(P.obs)[gi];   // polar only (macm_rollout checks)
             reinterpret_cast<float2*>(S.nw())[i] = make_float2(o4.z, o4.w);
+        }
+    }
+    if (bulk) {   // angles, sleep timers and (below) the action words have landed
+        mbar_wait(bar, 0);
+#pragma unroll
+        for (int s = 0; s < APL; ++s) {
+            const float2 as = reinterpret_cast<const float2*>(stg + N * 16)[valid[s] ? g.gl + s * G : 0];
+            ang[s] = as.x; slp[s] = as.y;
         }
     }
     const bool discrete = TDM || P.action_mode == MACM_ACTION_DISCRETE;
@@ -1098,7 +1171,8 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
         if (discrete && valid[s]) {
             if (!ROLL || actions) {
                 const uint32_t* aw = reinterpret_cast<const uint32_t*>(actions) + (size_t)ks * EN + gi;
-                act_raw[s] = *aw;
+                if (bulk && ks == 0) act_raw[s] = reinterpret_cast<const uint32_t*>(stg + N * 24)[i];
+                else act_raw[s] = *aw;
                 if (!last) asm volatile("prefetch.global.L2 [%0];" ::"l"(aw + EN));
             } else if (TDM && R.policy() == MACM_BOT_COMBAT) {
                 act_raw[s] = combat_action(pos, S.ang(), P.team, N, alive0, i);
@@ -1175,6 +1249,23 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
     // The bodies reach shared memory only now: phase 1 needs nothing but the angle and the action word, so the
     // rest of the state (positions, fat AABBs, contact list head, target) is still arriving from L2 while the
     // float64 action decode runs -- the whole batch loads its state at the same moment and the L2 is the queue.
+    if (bulk && ks == 0) {   // positions, velocities, fat AABBs and the head of the contact list have landed
+        mbar_wait(bar + 8, 0);
+#pragma unroll
+        for (int s = 0; s < APL; ++s) {
+            const int i = g.gl + s * G;
+            const float4 pv = reinterpret_cast<const float4*>(stg)[valid[s] ? i : 0];
+            c[s] = make_float2(pv.x, pv.y); v[s] = make_float2(pv.z, pv.w);
+            fatr[s] = fat[valid[s] ? i : 0];
+            if (!valid[s]) {  // padding agents: parked far away
+                c[s] = make_float2(3.0e30f, 3.0e30f); v[s] = make_float2(0.0f, 0.0f);
+                fatr[s] = make_float4(3.0e30f, 3.0e30f, 3.0e30f, 3.0e30f);
+            }
+        }
+        pre_ab = reinterpret_cast<const uint32_t*>(stg + N * 28)[g.gl];
+        pre_imp = reinterpret_cast<const float2*>(stg + N * 28 + 128)[g.gl];
+        g.sync();   // every lane has read its rows before a padding slot's fat AABB is overwritten below
+    }
 #pragma unroll
     for (int s = 0; s < APL; ++s) {
         const int i = g.gl + s * G;

@@ -49,6 +49,9 @@ struct SimConst {
     // outputs
     float* obs; int* nn_idx; float* rewards; uint8_t* collided; uint8_t* done;
     unsigned long long* trace;  // [E,4] per-env timing record (macm_set_trace), or null
+    // the env's state rows can travel to shared memory as 1-D bulk async copies (cp.async.bulk + mbarrier): one env
+    // per warp, Flock, discrete actions, N a multiple of 4, 16-byte aligned rows, room in the staging area
+    int bulk;
 };
 
 // Arguments of a multi-step launch (macm_rollout): K consecutive steps of every env inside one kernel, the env's

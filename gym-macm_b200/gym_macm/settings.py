@@ -60,7 +60,11 @@ class _EnvSettings(fwSettings):
         self.time_limit = 60
         self.bodySettings = {"fixtures": CircleFixture(0.5, 1, 0.3), "linearDamping": 5, "fixedRotation": True}
         # engine knobs the reference cannot express (pybox2d's Box2D version is unpinned)
-        self.damping_model = "taylor"      # "taylor": Box2D <= 2.3.0, "pade": >= 2.3.1
+        # Box2D changed its damping formula between 2.3.0 and 2.3.1 (0.7 % per step at the reference's settings).
+        # The reference calls ApplyForce(..., wake=) and installs pybox2d from pip, whose releases (Box2D 2.3.2+,
+        # box2d-py 2.3.5+) bundle the later engine: "pade" is the default.  tests/test_pybox2d_probe.py checks this
+        # against the real engine the day one is importable.
+        self.damping_model = "pade"        # "pade": v *= 1/(1 + h c), Box2D >= 2.3.1; "taylor": v *= clamp(1 - h c, 0, 1), <= 2.3.0
         self.max_contacts = 0              # 0 = library default
         self.max_touching = 0
         self.env_index_base = 0            # global index of this batch's env 0 (gym_macm.dist shards)

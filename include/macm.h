@@ -86,7 +86,7 @@ typedef struct macm_params {
     int32_t velocity_iterations;  /* settings.py:31   8 */
     int32_t position_iterations;  /* settings.py:32   3 */
     int32_t warm_starting;        /* settings.py:34   1 */
-    int32_t damping_model;        /* MACM_DAMPING_*   (pybox2d's engine version is unpinned) */
+    int32_t damping_model;        /* MACM_DAMPING_*   (pybox2d's engine version is unpinned; default PADE: pip releases bundle Box2D >= 2.3.1) */
     double radius;                /* settings.py:128  0.5 */
     double density;               /* settings.py:130  1 */
     double friction;              /* settings.py:131  0.3 */

@@ -96,7 +96,7 @@ def default_params(env_kind=FLOCK, n_agents=4, n_targets=1, **kw):
         radius=0.5, density=1.0, friction=0.3, linear_damping=5.0,
         agent_force=20.0, agent_rotation_speed=0.8 * (2 * np.pi), time_limit=60.0,
         reward_mode=0, action_mode=0, coord=0, reward_radius=7.0,
-        damping_model=0, warm_starting=1, flags=1,
+        damping_model=1, warm_starting=1, flags=1,
         cooldown_atk=1.0, cooldown_mov_penalty=0.5, melee_range=2.0, melee_dmg=0.25,
         percent_mov_penalty=0.2, init_health=1.0,
     )
@@ -232,7 +232,7 @@ class OracleBatch:
 class OracleWorld:
     """One world driven body by body, the way the reference drives pybox2d."""
 
-    def __init__(self, radius=0.5, density=1.0, friction=0.3, linear_damping=5.0, damping_model=0):
+    def __init__(self, radius=0.5, density=1.0, friction=0.3, linear_damping=5.0, damping_model=1):
         self._h = lib().oracle_world_create(radius, density, friction, linear_damping, damping_model)
         self.n = 0
 

@@ -180,7 +180,7 @@ class b2World(object):
         self.warmStarting, self.continuousPhysics, self.subStepping = True, True, False
         self.destructionListener = None
         self.contactListener = None
-        self.damping_model = int(__import__("os").environ.get("MACM_SHIM_DAMPING", "0"))   # 0 taylor, 1 pade
+        self.damping_model = int(__import__("os").environ.get("MACM_SHIM_DAMPING", "1"))   # 0 taylor, 1 pade (default, as gym_macm.settings)
 
     def CreateDynamicBody(self, fixtures=None, linearDamping=0.0, fixedRotation=False, position=(0, 0), angle=0.0,
                           userData=None, **kw):

@@ -60,7 +60,7 @@ def test_continuous_and_cartesian():
 
 
 def test_pade_damping_and_odd_iterations():
-    run_parity(32, 12, 60, seed=14, spread=4.0, damping_model="pade", velocityIterations=5, positionIterations=2)
+    run_parity(32, 12, 60, seed=14, spread=4.0, damping_model="taylor", velocityIterations=5, positionIterations=2)
     run_parity(32, 12, 30, seed=15, spread=4.0, positionIterations=0, enableWarmStarting=False)
 
 

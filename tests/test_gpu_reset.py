@@ -119,7 +119,11 @@ def test_tdm_envs_end_at_different_steps_and_reset_alone():
     ended_at = np.full(E, -1)
     n_resets = 0
     for k in range(900):
-        act = np.concatenate([rng.integers(0, 3, (E, N, 3)), (rng.random((E, N, 1)) < 0.9).astype(np.int64)], -1)
+        # the combat actor (bots.py:3-16) closes in and strikes, so matches do end; every 5th step is random
+        if k % 5:
+            act = env.bot_actions("combat").cpu().numpy().astype(np.int64)
+        else:
+            act = np.concatenate([rng.integers(0, 3, (E, N, 3)), (rng.random((E, N, 1)) < 0.9).astype(np.int64)], -1)
         env.step(torch.as_tensor(act, device="cuda:0"))
         o = ref.tdm_step(act)
         done = env.state["done"].cpu().numpy()

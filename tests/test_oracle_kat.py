@@ -38,9 +38,14 @@ def test_kat1_exact_constants(oracle_mod):
     assert mass == f32(0.7853982) and inv_mass == f32(1.2732395)
     v = f32(0) + h * (inv_mass * f32(20.0))
     v = v * (f32(1.0) - h * f32(5.0))
-    b = mk(oracle_mod, [[0, 0], FAR[0]], [0.0, 0.0])
+    b = mk(oracle_mod, [[0, 0], FAR[0]], [0.0, 0.0], damping_model=0)
     b.flock_step([[2, 1, 1], [1, 1, 1]])
     assert b.bodies()[0, 0, 2] == v
+    # the default model (Box2D >= 2.3.1): v *= 1 / (1 + h c)
+    vp = (f32(0) + h * (inv_mass * f32(20.0))) * (f32(1.0) / (f32(1.0) + h * f32(5.0)))
+    b = mk(oracle_mod, [[0, 0], FAR[0]], [0.0, 0.0])
+    b.flock_step([[2, 1, 1], [1, 1, 1]])
+    assert b.bodies()[0, 0, 2] == vp
 
 
 def test_kat2_damping_discriminator(oracle_mod):
@@ -125,7 +130,7 @@ def test_kat6_diagonal_action(oracle_mod):
     F = f32((np.cos(0.0) * 1 + np.cos(0.0 + np.pi / 2) * 1) * (1 / np.sqrt(2)) * 20)
     assert F == f32(14.142136)
     h = f32(1.0 / 60.0)
-    v = (f32(0) + h * (f32(1.2732395) * F)) * (f32(1.0) - h * f32(5.0))
+    v = (f32(0) + h * (f32(1.2732395) * F)) * (f32(1.0) / (f32(1.0) + h * f32(5.0)))   # default damping: Box2D >= 2.3.1
     assert s[2] == v and s[3] == v
 
 
@@ -191,8 +196,9 @@ def test_continuous_bug_compat(oracle_mod):
     y = np.sqrt(0.81 / (x * x + 0.81))
     assert abs(x - 0.7071) < 1e-4 and abs(y - 0.7863) < 1e-4
     h = f32(1.0 / 60.0)
-    vx = (f32(0) + h * (f32(1.2732395) * f32(x * 20))) * (f32(1.0) - h * f32(5.0))
-    vy = (f32(0) + h * (f32(1.2732395) * f32(y * 20))) * (f32(1.0) - h * f32(5.0))
+    damp = f32(1.0) / (f32(1.0) + h * f32(5.0))   # default damping: Box2D >= 2.3.1
+    vx = (f32(0) + h * (f32(1.2732395) * f32(x * 20))) * damp
+    vy = (f32(0) + h * (f32(1.2732395) * f32(y * 20))) * damp
     s = b.bodies()[0, 0]
     assert s[2] == vx and s[3] == vy
 
