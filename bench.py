@@ -358,7 +358,12 @@ def main():
     acts[..., :3] = torch.randint(0, 3, (POOL, E, N, 3), generator=g, device=dev, dtype=torch.uint8)
 
     NS = max(1, min(args.streams, ROT))
-    streams = [torch.cuda.Stream(device=dev) for _ in range(NS)] if NS > 1 else []
+    # gym_macm.BatchPool (the public API for this): the rotation's batches round-robin over NS streams of their own
+    pool = gym_macm.BatchPool(sims, n_streams=NS) if NS > 1 else None
+    streams = pool.streams if pool else []
+    if pool is None:
+        for s_ in sims:
+            s_.engine.stream = None
 
     def act_of(k):
         return acts[(k // ROT + 7 * (k % ROT)) % POOL]
@@ -366,18 +371,29 @@ def main():
     def step_on(strs):
         def issue(k):
             s = sims[k % ROT]
-            st = strs[(k % ROT) % len(strs)] if strs else None
+            st = strs[(k % ROT) % len(strs)] if strs else main_stream
             if args.policy == "flock":
-                with torch.cuda.stream(st if st is not None else main_stream):
+                with torch.cuda.stream(st):
                     a = s.bot_actions("flock")
             else:
                 a = act_of(k)
             s.engine.step(a, st)
         return issue
 
+    def pool_issue(k):           # the headline path: BatchPool.step
+        if args.policy == "flock":
+            s = sims[k % ROT]
+            with torch.cuda.stream(s.engine.stream):
+                a = s.bot_actions("flock")
+        else:
+            a = act_of(k)
+        pool.step(a)
+
     # settle: every batch runs SETTLE steps (1.07 s of simulated time of a 60 s / 3601-step episode)
     # so that the overlaps of the random spawn are resolved; then W warm-up steps of the rotation
-    issue, issue1 = step_on(streams), step_on([])
+    issue, issue1 = (pool_issue if pool else step_on([])), step_on([])
+    if pool:
+        pool.k = 0
     for k in range(args.settle * ROT):
         issue1(k)
     torch.cuda.synchronize()
@@ -386,12 +402,17 @@ def main():
     for k in range(args.warmup):
         issue(k)
     torch.cuda.synchronize()
+    if pool:
+        pool.k = 0
     launches0 = sum(s.engine.launch_count for s in sims)
     t0 = time.time()
     ms_win, ms_all, knext = T.windows(issue, K, NW, streams)
     t1 = time.time()
     launches = sum(s.engine.launch_count for s in sims) - launches0
     clocks = sampler.stop(t0, t1) if sampler else None
+    torch.cuda.synchronize()
+    for s_ in sims:                  # the legs below name their streams themselves
+        s_.engine.stream = None
     ms_per_step = ms_win / K
     value = world * E * N / (ms_per_step * 1e-3)
 
@@ -620,9 +641,9 @@ def other_configs(torch, gym_macm, T, dev, world, rank, K, NW, peak, settle):
         E = sims[0].engine.E
 
         def issue(k):
-            sims[k % ROT].engine.step(acts[(k // ROT + 3 * (k % ROT)) % POOL], st2[(k % ROT) & 1])
+            sims[k % ROT].engine.step(acts[(k // ROT + 7 * (k % ROT)) % POOL], st2[(k % ROT) & 1])
         for k in range(settle * ROT):
-            sims[k % ROT].engine.step(acts[(k // ROT + 3 * (k % ROT)) % POOL])
+            sims[k % ROT].engine.step(acts[(k // ROT + 7 * (k % ROT)) % POOL])
         torch.cuda.synchronize()
         T.windows(issue, min(steps, 4 * ROT), 1, st2)
         ms, _, _ = T.windows(issue, steps, NW, st2)
@@ -642,16 +663,16 @@ def other_configs(torch, gym_macm, T, dev, world, rank, K, NW, peak, settle):
     E3, N3 = 65536, 6
     sims = [gym_macm.BatchedFlock(E3, n_agents=[N3], targets=[0, 0, 1, 1, 2, 2], device=dev, seed=31 + 100 * rank + r)
             for r in range(10)]
-    acts = torch.zeros((7, E3, N3, 4), dtype=torch.uint8, device=dev)
-    acts[..., :3] = torch.randint(0, 3, (7, E3, N3, 3), generator=g, device=dev, dtype=torch.uint8)
+    acts = torch.zeros((31, E3, N3, 4), dtype=torch.uint8, device=dev)   # a prime pool: no short action cycle
+    acts[..., :3] = torch.randint(0, 3, (31, E3, N3, 3), generator=g, device=dev, dtype=torch.uint8)
     run("config3_multi_flock", sims, acts, N3, lambda c: b_alg_per_agent_step(c, 3, N3), K,
         "cm-flock-v0 6 agents, targets=[0,0,1,1,2,2], x 65536 envs per GPU, binary reward")
     del sims, acts
     # config 4: team deathmatch, 3 teams x 15 agents, 16,384 envs
     E4, N4 = 16384, 45
     sims = [gym_macm.BatchedTDM(E4, n_agents=[15, 15, 15], device=dev, seed=41 + 100 * rank + r) for r in range(2)]
-    acts = torch.randint(0, 3, (5, E4, N4, 4), generator=g, device=dev, dtype=torch.uint8)
-    acts[..., 3] = torch.randint(0, 2, (5, E4, N4), generator=g, device=dev, dtype=torch.uint8)
+    acts = torch.randint(0, 3, (17, E4, N4, 4), generator=g, device=dev, dtype=torch.uint8)
+    acts[..., 3] = torch.randint(0, 2, (17, E4, N4), generator=g, device=dev, dtype=torch.uint8)
     run("config4_tdm", sims, acts, N4, lambda c: 828.0 + 32.0 * c, max(4, min(K, 100)),
         "cm-tdm-v0 3 teams x 15 agents x 16384 envs per GPU, random actions with attacks")
     del sims, acts
@@ -659,8 +680,8 @@ def other_configs(torch, gym_macm, T, dev, world, rank, K, NW, peak, settle):
     E5, N5 = 32768, N_AGENTS
     sims = [gym_macm.BatchedFlock(E5, n_agents=[N5], reward_mode="linear", device=dev, seed=51 + 100 * rank + r)
             for r in range(2)]
-    acts = torch.zeros((3, E5, N5, 4), dtype=torch.uint8, device=dev)
-    acts[..., :3] = torch.randint(0, 3, (3, E5, N5, 3), generator=g, device=dev, dtype=torch.uint8)
+    acts = torch.zeros((31, E5, N5, 4), dtype=torch.uint8, device=dev)
+    acts[..., :3] = torch.randint(0, 3, (31, E5, N5, 3), generator=g, device=dev, dtype=torch.uint8)
     run("config5_32768_envs_per_gpu", sims, acts, N5, lambda c: b_alg_per_agent_step(c, 1, N5), max(4, min(K, 100)),
         "cm-flock-v0 64 agents x 32768 envs per GPU (%.1fM agents on %d GPUs), linear reward" % (world * E5 * N5 / 1e6, world))
     if world > 1:
@@ -670,7 +691,7 @@ def other_configs(torch, gym_macm, T, dev, world, rank, K, NW, peak, settle):
         peer = PeerGather(sims[0], world * E5, learner=0, names=("obs", "rewards", "done"))
 
         def peer_step(k):
-            sims[k % 2].engine.rollout(acts[k % 3], 1, None, 0, peer.mine[k & 1], st2[k & 1])
+            sims[k % 2].engine.rollout(acts[(k // 2 + 7 * (k % 2)) % 31], 1, None, 0, peer.mine[k & 1], st2[k & 1])
         T.windows(peer_step, 4, 1, st2)
         msp, _, _ = T.windows(peer_step, steps, max(3, NW // 3), st2)
         nb = (world - 1) * (E5 * N5 * 20 + E5)
@@ -683,7 +704,7 @@ def other_configs(torch, gym_macm, T, dev, world, rank, K, NW, peak, settle):
 
         def nccl_step(k):
             s = sims[k % 2]
-            s.engine.step(acts[k % 3])
+            s.engine.step(acts[(k // 2 + 7 * (k % 2)) % 31])
             gstream.wait_stream(T.main)
             with torch.cuda.stream(gstream):
                 dist.all_gather_into_tensor(gathered[0], s.state["obs"])

@@ -7,7 +7,7 @@ The ids of gym_macm/__init__.py:3-16 are registered with gym / gymnasium when on
 installed; `make` works either way.
 """
 from gym_macm import _lib, settings  # noqa: F401
-from gym_macm.batched import BatchedFlock, BatchedTDM  # noqa: F401
+from gym_macm.batched import BatchedFlock, BatchedTDM, BatchPool  # noqa: F401
 
 _ENTRY = {"cm-flock-v0": "gym_macm.envs:Flock", "cm-tdm-v0": "gym_macm.envs:TDM"}
 

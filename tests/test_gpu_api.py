@@ -277,3 +277,22 @@ def test_render_state_of_one_env():
     tdm = gym_macm.BatchedTDM(4, n_agents=[2, 2], device="cuda:0", seed=0)
     fr = tdm.render_state(1)
     assert [tuple(b.userData.color) for b in fr.world.bodies] == [(0.2, 0.2, 1.0)] * 2 + [(1.0, 0.2, 0.2)] * 2
+
+
+def test_batch_pool_equals_serial_stepping():
+    import torch
+    import gym_macm
+    E, N, K = 296, 64, 24
+    serial = [gym_macm.BatchedFlock(E, n_agents=[N], device="cuda:0", seed=60 + r) for r in range(3)]
+    pool = gym_macm.BatchPool([gym_macm.BatchedFlock(E, n_agents=[N], device="cuda:0", seed=60 + r) for r in range(3)])
+    acts = torch.zeros((K, E, N, 4), dtype=torch.uint8, device="cuda:0")
+    acts[..., :3] = torch.randint(0, 3, (K, E, N, 3), device="cuda:0", dtype=torch.uint8)
+    torch.cuda.synchronize()
+    for k in range(K):
+        serial[k % 3].step(acts[k])
+        assert pool.step(acts[k]) is pool.batches[k % 3]
+    pool.synchronize()
+    torch.cuda.synchronize()
+    for a, b in zip(serial, pool.batches):
+        for n in ("posvel", "angsleep", "fat", "obs", "nn_idx", "rewards", "contact_count"):
+            assert torch.equal(a.state[n], b.state[n]), n

@@ -14,6 +14,9 @@ import pytest
 
 from _parity import LIN_REWARD_ATOL, compare_obs
 
+from _parity import OBS_ATOL, OBS_RTOL, ang_diff
+from test_gpu_tdm import steps_left
+
 pytestmark = pytest.mark.gpu
 
 
@@ -146,4 +149,22 @@ def test_cfg4_full_size_tdm_subset():
         assert np.array_equal(st["done"][subt].cpu().numpy(), o["done"]), "step %d: done" % k
         obs = st["obs"][subt].cpu().numpy().reshape(n_sub, N, N, 4)
         assert np.array_equal(obs[..., 3].astype(np.int8), o["type"]), "step %d: ally/enemy/none flags" % k
+        # observation floats (combat.py:206-227; float64 in the reference, fp32 here: the bars of tests/_parity.py)
+        m = o["type"] >= 0
+        assert np.allclose(obs[..., 0][m], o["obs"][..., 0][m], rtol=OBS_RTOL, atol=OBS_ATOL), "step %d: obs r" % k
+        assert ang_diff(obs[..., 1][m].astype(np.float64), o["obs"][..., 1][m]).max() <= 3e-6, "step %d: obs theta" % k
+        assert ang_diff(obs[..., 2][m].astype(np.float64), o["obs"][..., 2][m]).max() <= 3e-6, "step %d: obs phi" % k
+        # cool-downs (whole steps left; combat.py:142,155) and alive flags
+        ti = st["tdm_state"][subt].cpu().view(torch.int32).numpy()
+        alive = ts[..., 3] > 0
+        assert np.array_equal(ti[..., 3] & 1, ts[..., 3].astype(np.int32)), "step %d: alive" % k
+        assert np.array_equal(ti[..., 1][alive], np.vectorize(steps_left)(ts[..., 1])[alive]), "step %d: attack cool-down" % k
+        assert np.array_equal(ti[..., 2][alive], np.vectorize(steps_left)(ts[..., 2])[alive]), "step %d: movement cool-down" % k
+        assert np.array_equal(st["env_state"][subt][:, 3].cpu().numpy(), o["winner"]), "step %d: winner" % k
+        # contact lists of the subset: pairs in birth order, touching flags, warm-start impulses
+        for j, e in enumerate(sub):
+            ab, fl, imp = env.contacts(int(e))
+            rab, rfl, rimp = ref.contacts(j)
+            assert np.array_equal(ab, rab) and np.array_equal(fl, rfl), "step %d env %d: contact list" % (k, e)
+            assert np.array_equal(imp[rfl.astype(bool)], rimp[rfl.astype(bool)]), "step %d env %d: impulses" % (k, e)
     env.close()
