@@ -426,18 +426,25 @@ def main():
         legs["one_stream"] = {"value": world * E * N * K / (ms1 * 1e-3), "unit": UNIT, "ms_per_step": ms1 / K,
                                "windows": NW, "note": "the same steps on one stream: no overlap between a batch's "
                                "tail (a few envs with long contact islands) and the next batch"}
-    # (2) one launch alone on an idle GPU (synchronised on both sides): the kernel's own duration
-    iso = []
+    # (2) one launch alone on an idle GPU (synchronised on both sides): the kernel's own duration, read from the
+    #     kernel's trace hook (macm_set_trace: every warp records %globaltimer at entry and exit; duration = last
+    #     exit - first entry, so no launch or event latency is in it)
+    iso = None
     if plain:
-        for k in range(40):
+        import ctypes as C
+        from gym_macm import _lib
+        trace = torch.zeros((E, 4), dtype=torch.int64, device=dev)
+        durs = []
+        for k in range(24):
+            s_ = sims[k % ROT]
+            _lib.check(_lib.lib().macm_set_trace(s_.engine._h, C.c_void_p(trace.data_ptr())))
             torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            sims[k % ROT].engine.step(act_of(knext + k))
-            e1.record()
+            s_.engine.step(act_of(knext + k))
             torch.cuda.synchronize()
-            iso.append(e0.elapsed_time(e1))
-        iso = T.max_over_ranks(statistics.median(iso[8:]))
+            _lib.check(_lib.lib().macm_set_trace(s_.engine._h, None))
+            durs.append(float(trace[:, 1].max() - trace[:, 0].min()) * 1e-6)   # ns -> ms
+        iso = T.max_over_ranks(statistics.median(durs[4:]))
+        del trace
     # (3) macm_rollout: R steps of a batch per launch, the envs' bodies held on chip between the steps; every
     #     step still writes its obs / nn_idx / rewards / collided / done (to per-step arrays).
     if plain and args.rollout > 0:
@@ -584,6 +591,8 @@ def main():
                                       "programmatic dependent launch, %d streams)" % NS}
         if iso:
             roofline["kernel_ms_isolated"] = iso
+            roofline["kernel_ms_isolated_kind"] = ("first warp entry to last warp exit (%globaltimer, macm_set_trace) of a "
+                                                    "launch alone on an idle, synchronised GPU; median of 20")
             roofline["frac_isolated"] = b_alg * E * N / (iso * 1e-3) / 1e9 / peak
         # what actually bounds the kernel (profiles/README.md): warp-instruction issue.  The instruction count is
         # the ncu figure of the committed capture; the peak is one instruction per clock on each of the SMs' four
