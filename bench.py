@@ -515,6 +515,7 @@ def main():
                                 "bytes_into_every_rank_per_step": (world - 1) * E * N * 20,
                                 "ingress_GBps": (world - 1) * E * N * 20 / (msn / K * 1e-3) / 1e9,
                                 "note": "NCCL all_gather_into_tensor of obs and rewards to every rank, on a side stream"}
+        peer.close()
         del gathered, peer
 
     # ---- the other BASELINE configs, each rotated over more than 2x L2 ----------------------------------------
@@ -727,6 +728,7 @@ def other_configs(torch, gym_macm, T, dev, world, rank, K, NW, peak, settle):
             "value": world * E5 * N5 * steps / (msn * 1e-3), "unit": UNIT, "ms_per_step": msn / steps,
             "bytes_into_every_rank_per_step": (world - 1) * E5 * N5 * 20,
             "ingress_GBps": (world - 1) * E5 * N5 * 20 / (msn / steps * 1e-3) / 1e9}
+        peer.close()
         del gathered, peer
     return out
 

@@ -210,6 +210,26 @@ class PeerGather(object):
         st.synchronize()
         dist.barrier(group=self.group)
 
+    def close(self):
+        """Collective: the shards unmap the learner's arrays (cudaIpcCloseMemHandle), then the learner frees them.
+        Call it before building another PeerGather whose arrays could reuse the same device addresses: CUDA refuses
+        to map an allocation that is still mapped from an earlier export ("resource already mapped")."""
+        import ctypes as C
+        from gym_macm import _lib
+        torch.cuda.synchronize(self.env.engine.device)
+        dist.barrier(group=self.group)
+        if self.rank != self.learner:
+            bases = set()
+            for full in self.full:
+                for t in full.values():
+                    bases.add(t.base)
+            for key, base in list(_OPENED.items()):
+                if base in bases:
+                    _lib.check(_lib.lib().macm_ipc_close(C.c_void_p(base)))
+                    del _OPENED[key]
+        dist.barrier(group=self.group)      # every mapping is gone before the learner's tensors are released
+        self.full, self.mine = [], []
+
     def gathered(self, back=1):
         """On the learner: the buffer set filled `back` steps ago (call fence() first)."""
         return self.full[(self.k - back) % len(self.full)]
