@@ -529,7 +529,9 @@ def main():
     # done inside the timed region, and the host reads a result before it issues the batch's next step.
     DEPTH = max(1, min(args.e2e_depth, ROT))
     pp = sims[:DEPTH] if args.e2e_steps > 0 else []
-    want = ("obs", "rewards", "done")
+    # what Flock.step returns (mvmnt.py:140,204-220): the observation nodes -- distances / angles AND the nearest
+    # agent's id -- and the rewards, plus env.done; the four arrays are contiguous in the output slab: one transfer
+    want = ("obs", "rewards", "done", "nn_idx")
     pin = pp[0].engine.pinned() if pp else {}
     host_actions = [acts[i].cpu().pin_memory() for i in range(4)]
     for s_ in pp:
@@ -556,7 +558,7 @@ def main():
            "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "d2h_transfers_per_step": 1,
            "pcie_GBps_per_gpu": (h2d + d2h) * args.e2e_steps / el / 1e9,
            "path": "macm_step_host_async/macm_host_sync on %d batches in rotation: pinned host actions -> device, "
-                   "step kernel, obs+rewards+done -> pinned host in ONE transfer (output slab)" % DEPTH}
+                   "step kernel, obs (floats + nearest-agent ids) + rewards + done -> pinned host in ONE transfer (output slab)" % DEPTH}
 
     if rank == 0:
         cpu = None

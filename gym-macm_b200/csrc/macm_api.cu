@@ -291,6 +291,7 @@ extern "C" int macm_create(macm_sim** out, const macm_params* p, int device)
     e = macm_launch_cfg(sim->K, sim->sm_count, &sim->cfg);
     if (e != cudaSuccess) { *out = nullptr; delete sim; return MACM_E_INVALID; }
     CU(macm_prepare_kernels(sim->K, sim->cfg, &sim->blocks_per_sm));
+    sim->K.first_wave = sim->sm_count * (sim->blocks_per_sm > 0 ? sim->blocks_per_sm : 1);
     // sin/cos(k/128), k = 0..417, as float64: the table behind the action decode's np.cos/np.sin
     {
         const int n = 418;

@@ -655,6 +655,10 @@ __device__ void flock_observe(const Grp<G>& g, const EnvS<G * APL>& S, const Sim
 // TDM.get_obs (combat.py:206-227): for every alive agent i, every other alive agent j:
 // [r, theta, phi] and the ally flag.  Row i of the [N,N,4] output is written by the whole group
 // (lane <-> j) so that the 16-byte stores of a row are contiguous.
+// The pass is the bulk of a TDM step (N^2 records of 16 bytes: 70 % of its instructions), so the row loop is kept
+// lean: one 16-byte header per agent (x, y, heading, team -- or -1 when it has no entry) staged where the fat AABBs
+// lived (dead by now, as in nn_search_64), one broadcast load per row, no branch inside the row (a record without
+// an entry is selected, not jumped around), row pointers advanced instead of recomputed.
 template <int G, int APL>
 __device__ void tdm_observe(const Grp<G>& g, const EnvS<G * APL>& S, const SimConst& P, int env, uint2 alive,
                             float* ob1, float* ob2)
@@ -662,38 +666,41 @@ __device__ void tdm_observe(const Grp<G>& g, const EnvS<G * APL>& S, const SimCo
     const float2* pos = S.pos();
     const float* angs = S.ang();
     const int N = P.N;
+    float4* hdr = S.fat();
     float2 o[APL];
-    float oa[APL];
-    int team[APL];
+    float oa[APL], code[APL];
+    g.sync();
 #pragma unroll
     for (int s = 0; s < APL; ++s) {
         const int j = g.gl + s * G;
         o[s] = pos[j];
         oa[s] = angs[j];
-        team[s] = j < N ? P.team[j] : 0;
+        code[s] = (j < N && bit_of(alive, j)) ? (float)P.team[j] : -1.0f;
+        hdr[j] = make_float4(o[s].x, o[s].y, oa[s], code[s]);
     }
-    float4* out = ob1 ? reinterpret_cast<float4*>(ob1) + (size_t)env * N * N : nullptr;
-    float4* out2 = ob2 ? reinterpret_cast<float4*>(ob2) + (size_t)env * N * N : nullptr;
+    g.sync();
+    float4* out = ob1 ? reinterpret_cast<float4*>(ob1) + (size_t)env * N * N + g.gl : nullptr;
+    float4* out2 = ob2 ? reinterpret_cast<float4*>(ob2) + (size_t)env * N * N + g.gl : nullptr;
+#pragma unroll 1
     for (int i = 0; i < N; ++i) {
-        const float2 p = pos[i];
-        const float a = angs[i];
-        const bool ai = bit_of(alive, i);
-        const int ti = P.team[i];
+        const float4 h = hdr[i];   // x, y, heading, team of the observer (-1: dead, observes nothing)
 #pragma unroll
         for (int s = 0; s < APL; ++s) {
             const int j = g.gl + s * G;
-            if (j >= N) continue;
-            float4 v = make_float4(0.0f, 0.0f, 0.0f, -1.0f);
-            if (ai && j != i && bit_of(alive, j)) {
-                const float dx = o[s].x - p.x, dy = o[s].y - p.y;
-                v.x = out_sqrtf(dx * dx + dy * dy);
-                v.y = wrap_pi_f(fast_atan2f(dy, dx) - a);
-                v.z = wrap_pi_f(oa[s] - a);
-                v.w = (team[s] == ti) ? 1.0f : 0.0f;
+            const float dx = o[s].x - h.x, dy = o[s].y - h.y;
+            const bool entry = h.w >= 0.0f && code[s] >= 0.0f && j != i;
+            float4 v;
+            v.x = entry ? out_sqrtf(dx * dx + dy * dy) : 0.0f;
+            v.y = entry ? wrap_pi_f(fast_atan2f(dy, dx) - h.z) : 0.0f;
+            v.z = entry ? wrap_pi_f(oa[s] - h.z) : 0.0f;
+            v.w = entry ? ((code[s] == h.w) ? 1.0f : 0.0f) : -1.0f;
+            if (j < N) {
+                if (out) out[s * G] = v;
+                if (out2) out2[s * G] = v;
             }
-            if (out) out[(size_t)i * N + j] = v;
-            if (out2) out2[(size_t)i * N + j] = v;
         }
+        if (out) out += N;
+        if (out2) out2 += N;
     }
 }
 
@@ -1002,7 +1009,10 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
     // from global memory before the wait; the env's lines are only pulled towards L2 (the coherence
     // point, so a line the predecessor is still writing cannot go stale there), which takes the HBM
     // latency of the state off the critical path whenever there is a predecessor to overlap with.
-    {
+    // (small-env shapes only: their launches are several waves of 128-thread blocks, and a block of a later wave gains
+    //  nothing from pulling lines it loads a few instructions later -- config 3: 27.5 -> 25.5 us.  The one-env-per-warp
+    //  kernel keeps the unconditional form: the same test there cost its zero-spill register allocation, +0.4 us.)
+    if (G == 32 || (int)blockIdx.x < P.first_wave) {
         // one line per lane: 8 lanes on posvel, 8 on the fat AABBs (or the TDM state after the first 4), 4 on
         // angle/sleep, 2 on the actions, 1 + 2 on the head of the contact list, then the per-env scalars.
         // (Everything before griddepcontrol.wait runs while the predecessor drains: a branch-free / table-driven

@@ -49,6 +49,9 @@ struct SimConst {
     // outputs
     float* obs; int* nn_idx; float* rewards; uint8_t* collided; uint8_t* done;
     unsigned long long* trace;  // [E,4] per-env timing record (macm_set_trace), or null
+    // blocks of the step kernel that are resident at once (SMs x blocks per SM): only those can overlap their L2
+    // prefetch with the predecessor's tail; a block of a later wave starts when its loads can be issued anyway
+    int first_wave;
     // the env's state rows can travel to shared memory as 1-D bulk async copies (cp.async.bulk + mbarrier): one env
     // per warp, Flock, discrete actions, N a multiple of 4, 16-byte aligned rows, room in the staging area
     int bulk;
