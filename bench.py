@@ -198,15 +198,15 @@ def run_reference(args, rank, world):
                              damping_model=DAMPING_CODE[default_damping()])
     ref.reset(pos, ang, targets=tg)
     acts = rng.integers(0, 3, (16, sample_envs, N_AGENTS, 3)).astype(np.int32)
-    for k in range(args.warmup):
+    for k in range(args.settle + args.warmup):      # the same 64 settle steps after the spawn as the GPU arm, untimed
         ref.flock_step(acts[k % 16], cores)
     t0 = time.perf_counter()
     for k in range(args.steps):
         ref.flock_step(acts[k % 16], cores)
     el = time.perf_counter() - t0
     val = sample_envs * N_AGENTS * args.steps / el
-    sample = "%d of the %d envs per step (x%d agents), %d steps, oracle port on %d threads" % (
-        sample_envs, N_ENVS, N_AGENTS, args.steps, cores)
+    sample = "%d of the %d envs per step (x%d agents), %d steps after %d settle steps, oracle port on %d threads" % (
+        sample_envs, N_ENVS, N_AGENTS, args.steps, args.settle, cores)
     kind = "port"
     if real and "agent_steps_per_sec" in real:
         # the real thing: pybox2d + the reference's Python host, single process (it has no batch axis)

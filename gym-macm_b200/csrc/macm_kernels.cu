@@ -175,7 +175,7 @@ __device__ __forceinline__ void prefetch_l2(int gl, const void* p, int bytes)
 // 1-D bulk asynchronous copies global -> shared memory, completion counted in bytes on an mbarrier (TMA unit, no
 // tensor map): the step kernel fetches an env's contiguous state rows with a handful of instructions on one lane.
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, int count)
+__device__ __forceinline__ __attribute__((unused)) void mbar_init(uint32_t bar, int count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -667,40 +667,37 @@ __device__ void tdm_observe(const Grp<G>& g, const EnvS<G * APL>& S, const SimCo
     const float* angs = S.ang();
     const int N = P.N;
     float4* hdr = S.fat();
-    float2 o[APL];
-    float oa[APL], code[APL];
     g.sync();
 #pragma unroll
     for (int s = 0; s < APL; ++s) {
         const int j = g.gl + s * G;
-        o[s] = pos[j];
-        oa[s] = angs[j];
-        code[s] = (j < N && bit_of(alive, j)) ? (float)P.team[j] : -1.0f;
-        hdr[j] = make_float4(o[s].x, o[s].y, oa[s], code[s]);
+        const float2 q = pos[j];
+        hdr[j] = make_float4(q.x, q.y, angs[j], (j < N && bit_of(alive, j)) ? (float)P.team[j] : -1.0f);
     }
     g.sync();
-    float4* out = ob1 ? reinterpret_cast<float4*>(ob1) + (size_t)env * N * N + g.gl : nullptr;
-    float4* out2 = ob2 ? reinterpret_cast<float4*>(ob2) + (size_t)env * N * N + g.gl : nullptr;
+    // The N x N records are walked in MEMORY order, G at a time (record r = i * N + j -> lane r % G): every store of
+    // the group is one contiguous run of 16-byte records whatever N is, and no lane idles on a ragged row end
+    // (N = 45 on 32 lanes: 64 rounds instead of 90).  i and j advance without a division.
+    const int total = N * N;
+    float4* out = ob1 ? reinterpret_cast<float4*>(ob1) + (size_t)env * total : nullptr;
+    float4* out2 = ob2 ? reinterpret_cast<float4*>(ob2) + (size_t)env * total : nullptr;
+    int i = g.gl / N, j = g.gl - i * N;          // G may exceed N (small teams on a wide group)
+    const int di = G / N, dj = G - di * N;       // one round further: G records
 #pragma unroll 1
-    for (int i = 0; i < N; ++i) {
-        const float4 h = hdr[i];   // x, y, heading, team of the observer (-1: dead, observes nothing)
-#pragma unroll
-        for (int s = 0; s < APL; ++s) {
-            const int j = g.gl + s * G;
-            const float dx = o[s].x - h.x, dy = o[s].y - h.y;
-            const bool entry = h.w >= 0.0f && code[s] >= 0.0f && j != i;
-            float4 v;
-            v.x = entry ? out_sqrtf(dx * dx + dy * dy) : 0.0f;
-            v.y = entry ? wrap_pi_f(fast_atan2f(dy, dx) - h.z) : 0.0f;
-            v.z = entry ? wrap_pi_f(oa[s] - h.z) : 0.0f;
-            v.w = entry ? ((code[s] == h.w) ? 1.0f : 0.0f) : -1.0f;
-            if (j < N) {
-                if (out) out[s * G] = v;
-                if (out2) out2[s * G] = v;
-            }
-        }
-        if (out) out += N;
-        if (out2) out2 += N;
+    for (int r = g.gl; r < total; r += G) {
+        const float4 h = hdr[i];   // observer: x, y, heading, team (-1: dead, observes nothing)
+        const float4 q = hdr[j];   // observed
+        const float dx = q.x - h.x, dy = q.y - h.y;
+        const bool entry = h.w >= 0.0f && q.w >= 0.0f && j != i;
+        float4 v;
+        v.x = entry ? out_sqrtf(dx * dx + dy * dy) : 0.0f;
+        v.y = entry ? wrap_pi_f(fast_atan2f(dy, dx) - h.z) : 0.0f;
+        v.z = entry ? wrap_pi_f(q.z - h.z) : 0.0f;
+        v.w = entry ? ((q.w == h.w) ? 1.0f : 0.0f) : -1.0f;
+        if (out) out[r] = v;
+        if (out2) out2[r] = v;
+        j += dj; i += di;
+        if (j >= N) { j -= N; ++i; }
     }
 }
 
