@@ -190,7 +190,7 @@ static int derive_constants(macm_sim* sim)
     TC = (TC + 15) / 16 * 16;
     // macm_rollout parks 20 bytes per agent slot in the (24-byte-per-entry) touching-contact stage between steps
     {
-        const int slots = p.n_agents > 32 ? 64 : (p.n_agents > 16 ? 32 : 16);
+        const int slots = p.n_agents > 64 ? 128 : (p.n_agents > 32 ? 64 : (p.n_agents > 16 ? 32 : 16));
         const int need = (20 * slots + 23) / 24;
         if (TC < need) TC = (need + 15) / 16 * 16;
     }

@@ -47,6 +47,17 @@
 
 namespace {
 
+// Agent sets: one bit per agent of an env.  Up to 64 agents: a uint2 (word = agent >> 5); 65..128 agents (four agents per
+// lane): four words.  Everything that existed before the wide shape keeps its uint2 code verbatim.
+struct Set4 { uint32_t w[4]; };
+template <int NC> struct SetOf { typedef uint2 type; };
+template <> struct SetOf<128> { typedef Set4 type; };
+template <typename T> __device__ __forceinline__ T empty_set();
+template <> __device__ __forceinline__ uint2 empty_set<uint2>() { return make_uint2(0u, 0u); }
+template <> __device__ __forceinline__ Set4 empty_set<Set4>() { Set4 r; r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0u; return r; }
+__device__ __forceinline__ bool set_nonzero(uint2 m) { return (m.x | m.y) != 0u; }
+__device__ __forceinline__ bool set_nonzero(const Set4& m) { return (m.w[0] | m.w[1] | m.w[2] | m.w[3]) != 0u; }
+
 // ------------------------------------------------------------------------------------------
 // shared-memory layout of one environment
 // ------------------------------------------------------------------------------------------
@@ -55,16 +66,17 @@ struct Lay {
     static constexpr int POS = 0;                 // float2 [NC]  centre
     static constexpr int VEL = POS + 8 * NC;      // float2 [NC]  linear velocity
     static constexpr int FAT = VEL + 8 * NC;      // float4 [NC]  fat AABB lo.xy hi.xy
-    static constexpr int ADJ = FAT + 16 * NC;     // uint2  [NC]  contact adjacency row (agents 0-31, 32-63)
+    static constexpr int ROWB = NC > 64 ? 16 : 8; // bytes of one agent-set row: 64 agents in a uint2, 128 in four words
+    static constexpr int ADJ = FAT + 16 * NC;     // set    [NC]  contact adjacency row (agents 0-31, 32-63, ...)
     // One 8-byte-per-agent scratch region, used by phases that never overlap in time:
     //   phase 1b  float2 [NC]  far end of an attacker's ray (TDM)
     //   phase 8   u32    [NC]  min sleep time of the island seeded here            (first half)
     //   phase 2a/10  uint2 [NC]  new-pair row being assembled (re-zeroed on entry)
     //   phase 12-13  float [NC]  body angle for the TDM observation pass           (second half)
-    static constexpr int NEW = ADJ + 8 * NC;
+    static constexpr int NEW = ADJ + ROWB * NC;
     static constexpr int ISLMIN = NEW;
     static constexpr int ANG = NEW + 4 * NC;
-    static constexpr int TGT = NEW + 8 * NC;      // float2 [NC]  the agent's target (Flock), staged with the state
+    static constexpr int TGT = NEW + ROWB * NC;   // float2 [NC]  the agent's target (Flock), staged with the state
     static constexpr int TMASK = TGT + 8 * NC;    // u32    [NC]  staged touching contacts (index < 32) of a body
     static constexpr int LABEL = TMASK + 4 * NC;  // u32    [NC]  island seed (highest body index of the island)
     static constexpr int STACK = LABEL + 4 * NC;  // u8     [NC]  DFS stack (intrusive next-pointers on the common path)
@@ -80,13 +92,19 @@ struct Lay {
     __host__ __device__ static constexpr int bytes(int TC) { return (FIXED + 24 * TC + 15) / 16 * 16; }
 };
 
-// edge word of a touching contact: a | b<<6 | next-of-a<<12 | next-of-b<<20 | taken<<28
-#define EW_A(w) ((int)((w) & 63u))
-#define EW_B(w) ((int)(((w) >> 6) & 63u))
-#define EW_NA(w) ((int)(((w) >> 12) & 255u))
-#define EW_NB(w) ((int)(((w) >> 20) & 255u))
-#define EW_TAKEN 0x10000000u
+// edge word of a touching contact: a | b<<B | next-of-a<<2B | next-of-b<<(2B+8) | taken<<(2B+16), B = 6 bits of body
+// index for envs of up to 64 agents (the constants every shape had before 128-agent envs existed), 7 beyond
 #define EW_NONE 255
+template <int NC>
+struct EW {
+    static constexpr int B = NC > 64 ? 7 : 6;
+    static constexpr uint32_t ID = (1u << B) - 1u, AB = (1u << (2 * B)) - 1u, TAKEN = 1u << (2 * B + 16);
+    static constexpr int SH_B = B, SH_NA = 2 * B, SH_NB = 2 * B + 8;
+    __device__ static int a(uint32_t w) { return (int)(w & ID); }
+    __device__ static int b(uint32_t w) { return (int)((w >> SH_B) & ID); }
+    __device__ static int na(uint32_t w) { return (int)((w >> SH_NA) & 255u); }
+    __device__ static int nb(uint32_t w) { return (int)((w >> SH_NB) & 255u); }
+};
 
 template <int NC>
 struct EnvS {
@@ -95,8 +113,9 @@ struct EnvS {
     __device__ float2* pos() const { return (float2*)(base + Lay<NC>::POS); }
     __device__ float2* vel() const { return (float2*)(base + Lay<NC>::VEL); }
     __device__ float4* fat() const { return (float4*)(base + Lay<NC>::FAT); }
-    __device__ uint2* adj() const { return (uint2*)(base + Lay<NC>::ADJ); }
-    __device__ uint2* nw() const { return (uint2*)(base + Lay<NC>::NEW); }
+    typedef typename SetOf<NC>::type SetT;
+    __device__ SetT* adj() const { return (SetT*)(base + Lay<NC>::ADJ); }
+    __device__ SetT* nw() const { return (SetT*)(base + Lay<NC>::NEW); }
     __device__ uint32_t* isl_min() const { return (uint32_t*)(base + Lay<NC>::ISLMIN); }
     __device__ float* ang() const { return (float*)(base + Lay<NC>::ANG); }
     __device__ float2* tgt() const { return (float2*)(base + Lay<NC>::TGT); }
@@ -154,6 +173,13 @@ __device__ __forceinline__ void or_bit(uint2* row, int r, int bit)
 {
     atomicOr(bit < 32 ? &row[r].x : &row[r].y, 1u << (bit & 31));
 }
+__device__ __forceinline__ bool bit_of(const Set4& m, int i) { return (m.w[i >> 5] >> (i & 31)) & 1u; }
+__device__ __forceinline__ void or_bit(Set4* row, int r, int bit) { atomicOr(&row[r].w[bit >> 5], 1u << (bit & 31)); }
+// the ballot of slot s (agents s*G .. s*G + G - 1) into an agent set that starts out empty
+template <int G>
+__device__ __forceinline__ void put_slot(uint2& m, int s, unsigned bm) { if (s == 0) m.x = bm; else m.y = bm; }
+template <int G>
+__device__ __forceinline__ void put_slot(Set4& m, int s, unsigned bm) { m.w[(s * G) >> 5] |= bm << ((s * G) & 31); }
 
 // Packed fp32x2 arithmetic of sm_100 (FADD2 / FMUL2): two IEEE round-to-nearest operations per
 // instruction, bit-identical to the scalar ones.  (A packed multiply feeding a packed add would be
@@ -432,6 +458,97 @@ __device__ int find_new_contacts(const Grp<G>& g, const EnvS<G * APL>& S, const 
     return base < P.C ? base : P.C;
 }
 
+// The same for envs of 65..128 agents (four words per set): rows and bit scans run over the words.
+template <int G, int APL>
+__device__ int find_new_contacts(const Grp<G>& g, const EnvS<G * APL>& S, const SimConst& P, const Set4& moved, const Set4& alive,
+                                 int cnt, uint32_t* c_ab, float2* c_imp, bool& overflow)
+{
+    const float4* fat = S.fat();
+    Set4* adj = S.adj();
+    Set4* nw = S.nw();
+    Set4 hit[APL];
+    float4 own[APL];
+#pragma unroll
+    for (int s = 0; s < APL; ++s) {
+        const int i = g.gl + s * G;
+        hit[s] = empty_set<Set4>();
+        own[s] = fat[i];
+        if (!bit_of(alive, i)) own[s] = make_float4(3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f);
+        nw[i] = empty_set<Set4>();
+    }
+    g.sync();
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        for (unsigned mm = moved.w[w]; mm; mm &= mm - 1) {
+            const int m = w * 32 + __ffs((int)mm) - 1;
+            const float4 mb = fat[m];
+            const unsigned bit = 1u << (m & 31);
+#pragma unroll
+            for (int s = 0; s < APL; ++s) {
+                const bool h = (g.gl + s * G != m) && aabb_overlap(mb, own[s]);
+                hit[s].w[w] |= h ? bit : 0u;
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < APL; ++s) {
+        const int i = g.gl + s * G;
+        if (!bit_of(moved, i)) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                unsigned lo = hit[s].w[w];
+                if (w == (i >> 5)) lo &= (1u << (i & 31)) - 1u;      // partners m < i only
+                if (w > (i >> 5)) lo = 0u;
+                for (; lo; lo &= lo - 1) or_bit(nw, w * 32 + __ffs((int)lo) - 1, i);
+            }
+        }
+    }
+    g.sync();
+    Set4 fresh[APL];
+    bool any = false;
+#pragma unroll
+    for (int s = 0; s < APL; ++s) {
+        const int i = g.gl + s * G;
+        const Set4 posted = nw[i], have = adj[i];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            unsigned row = hit[s].w[w];
+            if (w == (i >> 5)) row &= ~((2u << (i & 31)) - 1u);      // keep partners j > i only
+            if (w < (i >> 5)) row = 0u;
+            fresh[s].w[w] = (row | posted.w[w]) & ~have.w[w];
+        }
+        any |= set_nonzero(fresh[s]);
+    }
+    if (!g.ballot(any)) return cnt;
+    int base = cnt;
+#pragma unroll
+    for (int s = 0; s < APL; ++s) {
+        const int i = g.gl + s * G;
+        const int c = __popc(fresh[s].w[0]) + __popc(fresh[s].w[1]) + __popc(fresh[s].w[2]) + __popc(fresh[s].w[3]);
+        const int incl = g.scan_incl(c);
+        const int total = g.shfl(incl, G - 1);
+        int pos = base + incl - c;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            for (unsigned f = fresh[s].w[w]; f; f &= f - 1) {
+                const int j = w * 32 + __ffs((int)f) - 1;
+                if (pos < P.C) {
+                    c_ab[pos] = (uint32_t)i | ((uint32_t)j << 8);
+                    c_imp[pos] = make_float2(0.0f, 0.0f);
+                    or_bit(adj, i, j);
+                    or_bit(adj, j, i);
+                } else {
+                    overflow = true;
+                }
+                ++pos;
+            }
+        }
+        base += total;
+    }
+    g.sync();
+    return base < P.C ? base : P.C;
+}
+
 // ------------------------------------------------------------------------------------------
 // Nearest other agent for the two agents of a lane (N in 33..64; agents gl and gl + 32).
 //
@@ -660,8 +777,8 @@ __device__ void flock_observe(const Grp<G>& g, const EnvS<G * APL>& S, const Sim
 // lived (dead by now, as in nn_search_64), one broadcast load per row, no branch inside the row (a record without
 // an entry is selected, not jumped around), row pointers advanced instead of recomputed.
 template <int G, int APL>
-__device__ void tdm_observe(const Grp<G>& g, const EnvS<G * APL>& S, const SimConst& P, int env, uint2 alive,
-                            float* ob1, float* ob2)
+__device__ void tdm_observe(const Grp<G>& g, const EnvS<G * APL>& S, const SimConst& P, int env,
+                            const typename SetOf<G * APL>::type& alive, float* ob1, float* ob2)
 {
     const float2* pos = S.pos();
     const float* angs = S.ang();
@@ -710,6 +827,7 @@ template <int G, int APL>
 __device__ __noinline__ void solve_velocity_big(const Grp<G>& g, const EnvS<G * APL>& S, const SimConst& P, int tc,
                                                 int nlev, float ratio, float2* c_imp)
 {
+    using EWT = EW<G * APL>;
     const float2* pos = S.pos(); float2* vel = S.vel();
     float2* t_n = S.t_n(); float2* t_imp = S.t_imp();
     const uint32_t* t_ew = S.t_ew();
@@ -717,7 +835,7 @@ __device__ __noinline__ void solve_velocity_big(const Grp<G>& g, const EnvS<G * 
     const float mass_n = P.normal_mass, mass_t = P.normal_mass;
     for (int t = g.gl; t < tc; t += G) {
         const uint32_t ew = t_ew[t];
-        const float2 pa = pos[EW_A(ew)], pb = pos[EW_B(ew)];
+        const float2 pa = pos[EWT::a(ew)], pb = pos[EWT::b(ew)];
         float nx = 1.0f, ny = 0.0f;
         const float dx = pb.x - pa.x, dy = pb.y - pa.y;
         if ((dx * dx + dy * dy) > B2_EPSILON * B2_EPSILON) { nx = dx; ny = dy; b2normalize(nx, ny); }
@@ -734,7 +852,7 @@ __device__ __noinline__ void solve_velocity_big(const Grp<G>& g, const EnvS<G * 
                 if ((ol >> 8) != lev) continue;
                 const int t = ol & 0xff;
                 const uint32_t ew = t_ew[t];
-                const int a = EW_A(ew), b = EW_B(ew);
+                const int a = EWT::a(ew), b = EWT::b(ew);
                 const float2 n = t_n[t];
                 float2 im = t_imp[t];
                 float2 va = vel[a], vb = vel[b];
@@ -754,6 +872,7 @@ template <int G, int APL>
 __device__ __noinline__ void solve_position_big(const Grp<G>& g, const EnvS<G * APL>& S, const SimConst& P, int tc,
                                                 int nlev)
 {
+    using EWT = EW<G * APL>;
     float2* pos = S.pos();
     const uint32_t* label = S.label();
     uint8_t* isl_act = S.isl_act(); uint8_t* isl_bad = S.isl_bad();
@@ -768,7 +887,7 @@ __device__ __noinline__ void solve_position_big(const Grp<G>& g, const EnvS<G * 
                 const int ol = ordlvl[k];
                 if ((ol >> 8) != lev) continue;
                 const uint32_t ew = t_ew[ol & 0xff];
-                const int a = EW_A(ew), b = EW_B(ew);
+                const int a = EWT::a(ew), b = EWT::b(ew);
                 const int isl = label[a];
                 if (!isl_act[isl]) continue;
                 float2 ca = pos[a], cb = pos[b];
@@ -802,6 +921,7 @@ __device__ __noinline__ void solve_position_big(const Grp<G>& g, const EnvS<G * 
 template <int G, int APL>
 __device__ __noinline__ int islands_big(const Grp<G>& g, const EnvS<G * APL>& S, int tc)
 {
+    using EWT = EW<G * APL>;
     uint32_t* t_ew = S.t_ew();
     uint16_t* ordlvl = S.ordlvl();
     uint32_t* label = S.label();
@@ -811,31 +931,38 @@ __device__ __noinline__ int islands_big(const Grp<G>& g, const EnvS<G * APL>& S,
     int L = 1;
     if (g.gl == 0) {
         uint8_t* stack = S.stack(); uint8_t* head = S.head(); uint8_t* lastlvl = S.lastlvl();
-        uint32_t rem_lo = 0u, rem_hi = 0u;   // bodies with a touching contact that are not in an island yet
+        constexpr int W = (G * APL + 31) / 32 < 2 ? 2 : (G * APL + 31) / 32;
+        uint32_t rem[W];   // bodies with a touching contact that are not in an island yet
+#pragma unroll
+        for (int w = 0; w < W; ++w) rem[w] = 0u;
         for (int t = 0; t < tc; ++t) {
             const uint32_t ew = t_ew[t];
-            const int a = EW_A(ew), b = EW_B(ew);
-            t_ew[t] = ew | ((uint32_t)head[a] << 12) | ((uint32_t)head[b] << 20);
+            const int a = EWT::a(ew), b = EWT::b(ew);
+            t_ew[t] = ew | ((uint32_t)head[a] << EWT::SH_NA) | ((uint32_t)head[b] << EWT::SH_NB);
             head[a] = (uint8_t)t;
             head[b] = (uint8_t)t;
-            if (a < 32) rem_lo |= 1u << a; else rem_hi |= 1u << (a - 32);
-            if (b < 32) rem_lo |= 1u << b; else rem_hi |= 1u << (b - 32);
+            rem[a >> 5] |= 1u << (a & 31);
+            rem[b >> 5] |= 1u << (b & 31);
         }
         int nord = 0;
-        while (rem_lo | rem_hi) {
-            const int seed = rem_hi ? (63 - __clz((int)rem_hi)) : (31 - __clz((int)rem_lo));
+        for (;;) {
+            int seed = -1;   // the highest body left: Box2D walks its body list from the last-created body
+#pragma unroll
+            for (int w = W - 1; w >= 0; --w)
+                if (seed < 0 && rem[w]) seed = w * 32 + 31 - __clz((int)rem[w]);
+            if (seed < 0) break;
             int sp = 0;
             stack[sp++] = (uint8_t)seed;
-            if (seed < 32) rem_lo &= ~(1u << seed); else rem_hi &= ~(1u << (seed - 32));
+            rem[seed >> 5] &= ~(1u << (seed & 31));
             while (sp > 0) {
                 const int b = stack[--sp];
                 label[b] = (uint32_t)seed;
                 for (int t = head[b]; t != EW_NONE;) {
                     const uint32_t ew = t_ew[t];
-                    const int ta = EW_A(ew), tb = EW_B(ew);
-                    const int nx = (ta == b) ? EW_NA(ew) : EW_NB(ew);
-                    if (!(ew & EW_TAKEN)) {
-                        t_ew[t] = ew | EW_TAKEN;
+                    const int ta = EWT::a(ew), tb = EWT::b(ew);
+                    const int nx = (ta == b) ? EWT::na(ew) : EWT::nb(ew);
+                    if (!(ew & EWT::TAKEN)) {
+                        t_ew[t] = ew | EWT::TAKEN;
                         const int l = 1 + max((int)lastlvl[ta], (int)lastlvl[tb]);
                         ordlvl[nord++] = (uint16_t)(t | (l << 8));
                         lastlvl[ta] = (uint8_t)l;
@@ -843,8 +970,7 @@ __device__ __noinline__ int islands_big(const Grp<G>& g, const EnvS<G * APL>& S,
                         L = max(L, l);
                         const int other = (ta == b) ? tb : ta;
                         const uint32_t ob = 1u << (other & 31);
-                        if (other < 32) { if (rem_lo & ob) { rem_lo &= ~ob; stack[sp++] = (uint8_t)other; } }
-                        else { if (rem_hi & ob) { rem_hi &= ~ob; stack[sp++] = (uint8_t)other; } }
+                        if (rem[other >> 5] & ob) { rem[other >> 5] &= ~ob; stack[sp++] = (uint8_t)other; }
                     }
                     t = nx;
                 }
@@ -859,10 +985,12 @@ __device__ __noinline__ int islands_big(const Grp<G>& g, const EnvS<G * APL>& S,
 // b2World::Step prologue of a world with new fixtures: FindNewContacts before Collide.  Runs on
 // the first step after a reset only; out of line.
 template <int G, int APL>
-__device__ __noinline__ int fresh_world_contacts(const Grp<G>& g, const EnvS<G * APL>& S, const SimConst& P, uint2 alive,
-                                                 int cnt, uint32_t* c_ab, float2* c_imp, bool& overflow)
+__device__ __noinline__ int fresh_world_contacts(const Grp<G>& g, const EnvS<G * APL>& S, const SimConst& P,
+                                                 typename SetOf<G * APL>::type alive, int cnt, uint32_t* c_ab, float2* c_imp,
+                                                 bool& overflow)
 {
-    uint2* adj = S.adj();
+    typedef typename SetOf<G * APL>::type SetT;
+    SetT* adj = S.adj();
     for (int base = 0; base < cnt; base += G) {
         const int k = base + g.gl;
         if (k < cnt) {
@@ -874,7 +1002,7 @@ __device__ __noinline__ int fresh_world_contacts(const Grp<G>& g, const EnvS<G *
     g.sync();
     cnt = find_new_contacts<G, APL>(g, S, P, alive, alive, cnt, c_ab, c_imp, overflow);
 #pragma unroll
-    for (int s = 0; s < APL; ++s) adj[g.gl + s * G] = make_uint2(0u, 0u);
+    for (int s = 0; s < APL; ++s) adj[g.gl + s * G] = empty_set<SetT>();
     g.sync();
     return cnt;
 }
@@ -919,8 +1047,9 @@ __device__ __noinline__ uint32_t bot_action(const SimConst& P, const Rollout& R,
 // from the staged positions and angles with the arithmetic of tdm_observe, so the choice is the one
 // macm_bot_kernel makes from the `obs` buffer: nearest enemy (lowest index among equal r), turn towards it,
 // walk when it is within +-36 degrees, strike inside 3 m.
+template <typename SetT>
 __device__ __noinline__ uint32_t combat_action(const float2* pos, const float* angs, const uint8_t* team, int N,
-                                               uint2 alive, int i)
+                                               SetT alive, int i)
 {
     uint32_t a0 = 1, a2 = 1, a3 = 0;
     if (i < N && bit_of(alive, i)) {
@@ -953,8 +1082,12 @@ __device__ __noinline__ uint32_t combat_action(const float2* pos, const float* a
 // MODE 2: one step per launch whose outputs ALSO go to the caller's per-step arrays (macm_rollout with n_steps = 1
 //         and given actions -- the shape gym_macm.dist.PeerGather uses to store into the learner's memory): the
 //         single-step code plus the second stores, none of the loop-carried state of MODE 1.
+// widest block of a shape: 28 warps of one env each; envs of 65..128 agents (four agents per lane) take 14 warps with
+// twice the registers per thread
+__host__ __device__ constexpr int shape_max_threads(int G, int APL) { return APL == 4 ? MACM_WIDE_THREADS / 2 : MACM_WIDE_THREADS; }
+
 template <int G, int APL, int KIND, int MODE>
-__global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const __grid_constant__ SimConst P,
+__global__ void __launch_bounds__(shape_max_threads(G, APL), 1) macm_step_kernel(const __grid_constant__ SimConst P,
                                                         const void* __restrict__ actions,
                                                         const __grid_constant__ Rollout R_)
 {
@@ -975,6 +1108,7 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
     constexpr int NC = G * APL;
     constexpr int GPW = 32 / G;
     constexpr bool TDM = KIND == MACM_ENV_TDM;
+    using EWT = EW<NC>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Grp<G> g;
     const int slot_in_block = (threadIdx.x >> 5) * GPW + (threadIdx.x & 31) / G;
@@ -997,7 +1131,8 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
     S.base = smem_raw + (size_t)slot_in_block * Lay<NC>::bytes(P.TC);
 
     float2* pos = S.pos(); float2* vel = S.vel(); float4* fat = S.fat();
-    uint2* adj = S.adj();
+    typedef typename SetOf<NC>::type ASet;
+    ASet* adj = S.adj();
     uint32_t* label = S.label();
     uint32_t* tmask = S.tmask();
 
@@ -1144,14 +1279,14 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
 #pragma unroll 1
     for (int ks = 0; ks < R.K(); ++ks) {
     const bool last = ks == R.K() - 1;
-    uint2 alive = make_uint2(0u, 0u);   // bodies that are active (have a proxy) during this step
+    ASet alive = empty_set<ASet>();   // bodies that are active (have a proxy) during this step
     // The block's warps start every R.sync()-th step together.  Measured (profiles/README.md, finding 8): the hot
     // path is ~48 KB of straight-line code; warps that drift apart each stream it from the GPC-level instruction
     // cache on their own, which saturates (gcc requests 83 % of peak, "no instruction" the top stall) -- in step
     // they share every fetched line.
     if (R.sync() > 0 && ks > 0 && (ks % R.sync()) == 0) __syncthreads();
     g.sync();   // the previous step's observation pass has finished reading the staging arrays
-    uint2 alive0 = make_uint2(0u, 0u);   // (combat actor) who is in the observation the actors decide on
+    ASet alive0 = empty_set<ASet>();   // (combat actor) who is in the observation the actors decide on
     if (ROLL && TDM && R.policy() == MACM_BOT_COMBAT) {
         if (ks == 0) {   // later steps: positions and angles are staged since the previous step's phases 7 and 11
 #pragma unroll
@@ -1160,7 +1295,7 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
 #pragma unroll
         for (int s = 0; s < APL; ++s) {
             const unsigned bm = g.ballot(was_alive[s]);
-            if (s == 0) alive0.x = bm; else alive0.y = bm;
+            put_slot<G>(alive0, s, bm);
         }
         g.sync();
     }
@@ -1278,7 +1413,7 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
         const int i = g.gl + s * G;
         pos[i] = c[s];
         fat[i] = fatr[s];
-        adj[i] = make_uint2(0u, 0u);
+        adj[i] = empty_set<ASet>();
         S.tmask()[i] = 0u;
         if (!TDM && !ROLL) S.tgt()[i] = tg0[s];
     }
@@ -1352,7 +1487,7 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
 #pragma unroll
     for (int s = 0; s < APL; ++s) {
         const unsigned bm = g.ballot(now_alive[s]);
-        if (s == 0) alive.x = bm; else alive.y = bm;
+        put_slot<G>(alive, s, bm);
     }
 
     bool overflow_c = false, overflow_t = false;
@@ -1403,7 +1538,7 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
                 or_bit(adj, a, b);
                 or_bit(adj, b, a);
                 if (touch && tp < P.TC) {
-                    t_ew[tp] = (uint32_t)a | ((uint32_t)b << 6);
+                    t_ew[tp] = (uint32_t)a | ((uint32_t)b << EWT::SH_B);
                     t_imp[tp] = make_float2(nI, tI);
                     t_slot[tp] = (uint16_t)p;
                     // the body's set of touching contacts; does any body carry two?
@@ -1474,7 +1609,7 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
         // pre-integration positions, impulses scaled by dtRatio
         if (has) {
             const uint32_t ew = t_ew[g.gl];
-            ka = EW_A(ew); kb = EW_B(ew);
+            ka = EWT::a(ew); kb = EWT::b(ew);
             const float2 pa = pos[ka], pb = pos[kb];
             const float dx = pb.x - pa.x, dy = pb.y - pa.y;
             // b2DistanceSquared(pointA, pointB) is (A - B).(A - B); squares are sign-blind
@@ -1537,10 +1672,12 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
                 oseed = seed;
                 uint8_t* nxt = S.stack();
                 uint32_t taken = 0u, vis_lo = 0u, vis_hi = 0u;
+                uint32_t vis_w2 = 0u, vis_w3 = 0u;   // (agents 64..127 of the wide shape)
                 int top = oseed, otail = EW_NONE;
                 uint32_t otail_ew = 0u;
                 nxt[oseed] = EW_NONE;
-                if (oseed < 32) vis_lo = 1u << oseed; else vis_hi = 1u << (oseed - 32);
+                if (NC <= 64 || oseed < 64) { if (oseed < 32) vis_lo = 1u << oseed; else vis_hi = 1u << (oseed - 32); }
+                else if (oseed < 96) vis_w2 = 1u << (oseed - 64); else vis_w3 = 1u << (oseed - 96);
                 while (top != EW_NONE) {
                     const int b = top;
                     top = nxt[b];
@@ -1548,20 +1685,22 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
                         const int t = 31 - __clz((int)m);   // newest edge first
                         m &= ~(1u << t);
                         taken |= 1u << t;
-                        const uint32_t ew = t_ew[t] & 0xfffu;
-                        if (otail == EW_NONE) ohead = t; else t_ew[otail] = otail_ew | ((uint32_t)t << 12);
+                        const uint32_t ew = t_ew[t] & EWT::AB;
+                        if (otail == EW_NONE) ohead = t; else t_ew[otail] = otail_ew | ((uint32_t)t << EWT::SH_NA);
                         otail = t; otail_ew = ew;
-                        const int other = (EW_A(ew) == b) ? EW_B(ew) : EW_A(ew);
+                        const int other = (EWT::a(ew) == b) ? EWT::b(ew) : EWT::a(ew);
                         const uint32_t ob = 1u << (other & 31);
-                        const bool seen = ((other < 32 ? vis_lo : vis_hi) & ob) != 0u;
+                        bool seen = ((other < 32 ? vis_lo : vis_hi) & ob) != 0u;
+                        if (NC > 64 && other >= 64) seen = ((other < 96 ? vis_w2 : vis_w3) & ob) != 0u;
                         if (!seen) {
-                            if (other < 32) vis_lo |= ob; else vis_hi |= ob;
+                            if (NC <= 64 || other < 64) { if (other < 32) vis_lo |= ob; else vis_hi |= ob; }
+                            else if (other < 96) vis_w2 |= ob; else vis_w3 |= ob;
                             nxt[other] = (uint8_t)top;
                             top = other;
                         }
                     }
                 }
-                t_ew[otail] = otail_ew | ((uint32_t)EW_NONE << 12);
+                t_ew[otail] = otail_ew | ((uint32_t)EW_NONE << EWT::SH_NA);
 #ifdef MACM_PHASE_TRACE
                 dfs_done = clock64() - tr_c0;
 #endif
@@ -1574,7 +1713,7 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
                     uint32_t ew = ew_head;
                     float2 n = n_head, im = t_imp[t];
                     for (;;) {
-                        const int a = EW_A(ew), b = EW_B(ew), tn = EW_NA(ew);
+                        const int a = EWT::a(ew), b = EWT::b(ew), tn = EWT::na(ew);
                         float2 va = vel[a], vb = vel[b];
                         uint32_t ew2 = 0u;
                         float2 n2 = make_float2(0.0f, 0.0f), im2 = n2;
@@ -1649,7 +1788,7 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
                 float min_sep = 0.0f;
                 uint32_t ew = ew_head;
                 for (;;) {
-                    const int a = EW_A(ew), b = EW_B(ew), tn = EW_NA(ew);
+                    const int a = EWT::a(ew), b = EWT::b(ew), tn = EWT::na(ew);
                     float2 ca = pos[a], cb = pos[b];
                     uint32_t ew2 = 0u;
                     if (tn != EW_NONE) ew2 = t_ew[tn];
@@ -1703,7 +1842,7 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
 
     PHASE_STAMP(8);
     // ---- phase 9: SynchronizeFixtures -> b2DynamicTree::MoveProxy -----------------------------------
-    uint2 moved = make_uint2(0u, 0u);
+    ASet moved = empty_set<ASet>();
 #pragma unroll
     for (int s = 0; s < APL; ++s) {
         const int i = g.gl + s * G;
@@ -1722,13 +1861,13 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
             fat[i] = fatr[s];
         }
         const unsigned bm = g.ballot(mv);
-        if (s == 0) moved.x = bm; else moved.y = bm;
+        put_slot<G>(moved, s, bm);
     }
     g.sync();
 
     PHASE_STAMP(9);
     // ---- phase 10: FindNewContacts ------------------------------------------------------------------
-    if (moved.x | moved.y) cnt = find_new_contacts<G, APL>(g, S, P, moved, alive, cnt, c_ab, c_imp, overflow_c);
+    if (set_nonzero(moved)) cnt = find_new_contacts<G, APL>(g, S, P, moved, alive, cnt, c_ab, c_imp, overflow_c);
 
     PHASE_STAMP(10);
     // ---- phase 11: rewards (mvmnt.py:160-179), time/done (mvmnt.py:134-136) ---------------------------
@@ -1751,8 +1890,7 @@ __global__ void __launch_bounds__(MACM_WIDE_THREADS, 1) macm_step_kernel(const _
         const int i = g.gl + s * G;
         if (!valid[s]) continue;
         const size_t gi = (size_t)env * N + i;
-        const uint2 row = adj[i];
-        const bool col = (row.x | row.y) != 0;
+        const bool col = set_nonzero(adj[i]);
         float rew = -1.0f;
         if (TDM) {
             rew = (now_alive[s] && col) ? -1.0f : 0.0f;
@@ -1891,7 +2029,7 @@ __global__ void __launch_bounds__(128) macm_observe_kernel(const __grid_constant
         g.sync();   // the group's stores (targets) are visible to its lanes below
     }
     float ang[APL];
-    uint2 alive = make_uint2(0u, 0u);
+    typename SetOf<NC>::type alive = empty_set<typename SetOf<NC>::type>();
 #pragma unroll
     for (int s = 0; s < APL; ++s) {
         const int i = g.gl + s * G;
@@ -1911,7 +2049,7 @@ __global__ void __launch_bounds__(128) macm_observe_kernel(const __grid_constant
         bool al = ok;
         if (KIND == MACM_ENV_TDM) al = ok && (__float_as_int(P.tdm[gi].w) & 1);
         const unsigned bm = g.ballot(al);
-        if (s == 0) alive.x = bm; else alive.y = bm;
+        put_slot<G>(alive, s, bm);
     }
     g.sync();
     if (KIND == MACM_ENV_TDM) tdm_observe<G, APL>(g, S, P, env, alive, P.obs, nullptr);
@@ -2007,7 +2145,8 @@ static void pick_shape(int N, int* G, int* APL)
     else if (N <= 8) { *G = 8; *APL = 1; }
     else if (N <= 16) { *G = 16; *APL = 1; }
     else if (N <= 32) { *G = 32; *APL = 1; }
-    else { *G = 32; *APL = 2; }
+    else if (N <= 64) { *G = 32; *APL = 2; }
+    else { *G = 32; *APL = 4; }
 }
 
 cudaError_t macm_launch_cfg(const SimConst& P, int sm_count, LaunchCfg* cfg)
@@ -2017,15 +2156,16 @@ cudaError_t macm_launch_cfg(const SimConst& P, int sm_count, LaunchCfg* cfg)
     cfg->threads = 128;
     // one-env-per-warp groups: a block per SM (profiles/README.md, finding 4) unless the last wave of such
     // blocks would leave most SMs idle
-    const int wide_warps = MACM_WIDE_THREADS / 32;
+    const int wide_threads = shape_max_threads(cfg->G, cfg->APL);
+    const int wide_warps = wide_threads / 32;
     if (gpw == 1 && sm_count > 0 && P.E >= wide_warps) {
         const int wb = (P.E + wide_warps - 1) / wide_warps;
         const int waves = (wb + sm_count - 1) / sm_count;
-        if (wb * 5 >= waves * sm_count * 4) cfg->threads = MACM_WIDE_THREADS;   // >= 80 % of the slots used
+        if (wb * 5 >= waves * sm_count * 4) cfg->threads = wide_threads;   // >= 80 % of the slots used
     }
     if (const char* e = getenv("MACM_BLOCK_THREADS")) {   // experiments (profiles/README.md): 128 or 896
         const int t = atoi(e);
-        if (t == 128 || (t > 128 && t <= MACM_WIDE_THREADS && t % 32 == 0)) cfg->threads = t;
+        if (t == 128 || (t > 128 && t <= wide_threads && t % 32 == 0)) cfg->threads = t;
     }
     cfg->envs_per_block = (cfg->threads / 32) * gpw;
     cfg->blocks = (P.E + cfg->envs_per_block - 1) / cfg->envs_per_block;
@@ -2036,7 +2176,8 @@ cudaError_t macm_launch_cfg(const SimConst& P, int sm_count, LaunchCfg* cfg)
         case 8: per_env = Lay<8>::bytes(P.TC); break;
         case 16: per_env = Lay<16>::bytes(P.TC); break;
         case 32: per_env = Lay<32>::bytes(P.TC); break;
-        default: per_env = Lay<64>::bytes(P.TC); break;
+        case 64: per_env = Lay<64>::bytes(P.TC); break;
+        default: per_env = Lay<128>::bytes(P.TC); break;
     }
     cfg->per_env_bytes = per_env;
     if (per_env * cfg->envs_per_block + MACM_TABLE_BYTES > 227 * 1024) {   // fall back to narrow blocks
@@ -2057,11 +2198,13 @@ cudaError_t macm_launch_cfg(const SimConst& P, int sm_count, LaunchCfg* cfg)
         case (16 * 8 + 1) * 2: return CALL(16, 1, MACM_ENV_FLOCK);                  \
         case (32 * 8 + 1) * 2: return CALL(32, 1, MACM_ENV_FLOCK);                  \
         case (32 * 8 + 2) * 2: return CALL(32, 2, MACM_ENV_FLOCK);                  \
+        case (32 * 8 + 4) * 2: return CALL(32, 4, MACM_ENV_FLOCK);                  \
         case (4 * 8 + 1) * 2 + 1: return CALL(4, 1, MACM_ENV_TDM);                  \
         case (8 * 8 + 1) * 2 + 1: return CALL(8, 1, MACM_ENV_TDM);                  \
         case (16 * 8 + 1) * 2 + 1: return CALL(16, 1, MACM_ENV_TDM);                \
         case (32 * 8 + 1) * 2 + 1: return CALL(32, 1, MACM_ENV_TDM);                \
         case (32 * 8 + 2) * 2 + 1: return CALL(32, 2, MACM_ENV_TDM);                \
+        case (32 * 8 + 4) * 2 + 1: return CALL(32, 4, MACM_ENV_TDM);                \
         default: return cudaErrorInvalidConfiguration;                              \
     }
 

@@ -32,7 +32,8 @@ extern "C" {
 #endif
 
 #define MACM_ABI_VERSION 3
-#define MACM_MAX_AGENTS 64   /* per environment (contact adjacency is a 64-bit row per agent) */
+#define MACM_MAX_AGENTS 128  /* per environment (the reference has no cap, mvmnt.py:61); up to 64: two agents per lane,
+                                beyond: four, with 128-bit contact adjacency rows */
 #define MACM_MAX_TARGETS 16
 #define MACM_MAX_TEAMS 8
 

@@ -59,7 +59,7 @@
 #define B2_TIME_TO_SLEEP 0.5f
 #define B2_LINEAR_SLEEP_TOLERANCE 0.01f
 
-#define O_MAX_BODIES 64
+#define O_MAX_BODIES 128
 
 typedef struct { float x, y; } V2;
 
@@ -120,11 +120,12 @@ typedef struct {
     int last_touching, last_islands_multi;
 } OWorld;
 
-static void ow_init(OWorld* w, double radius, double density, double friction, double linear_damping,
+static void ow_init(OWorld* w, int max_bodies, double radius, double density, double friction, double linear_damping,
                     int damping_model, int warm_starting)
 {
     memset(w, 0, sizeof(*w));
-    w->ct_cap = O_MAX_BODIES * (O_MAX_BODIES - 1) / 2;
+    if (max_bodies < 2) max_bodies = 2;
+    w->ct_cap = max_bodies * (max_bodies - 1) / 2;    /* every pair of the world's bodies can hold a contact */
     w->ct = (OContact*)calloc((size_t)w->ct_cap, sizeof(OContact));
     for (int i = 0; i < w->ct_cap; ++i) w->ct[i].next = i + 1;
     w->ct[w->ct_cap - 1].next = -1;
@@ -702,7 +703,8 @@ OBatch* oracle_create(const OParams* p, int n_envs)
     B->n_envs = n_envs;
     B->e = (OEnv*)calloc((size_t)n_envs, sizeof(OEnv));
     for (int i = 0; i < n_envs; ++i)
-        ow_init(&B->e[i].w, p->radius, p->density, p->friction, p->linear_damping, p->damping_model, p->warm_starting);
+        ow_init(&B->e[i].w, p->n_agents, p->radius, p->density, p->friction, p->linear_damping, p->damping_model,
+                p->warm_starting);
     return B;
 }
 
@@ -1138,7 +1140,7 @@ OBatch* oracle_world_create(double radius, double density, double friction, doub
 {
     OParams p;
     memset(&p, 0, sizeof(p));
-    p.n_agents = 1; p.n_targets = 1; p.hz = 60.0; p.radius = radius; p.density = density; p.friction = friction;
+    p.n_agents = O_MAX_BODIES; p.n_targets = 1; p.hz = 60.0; p.radius = radius;   /* room for every body add_body may create */ p.density = density; p.friction = friction;
     p.linear_damping = linear_damping; p.damping_model = damping_model; p.warm_starting = 1;
     return oracle_create(&p, 1);
 }

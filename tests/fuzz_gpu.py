@@ -61,7 +61,7 @@ def main():
     while time.time() - t0 < args.seconds:
         if rng.random() < args.tdm:
             n_teams = int(rng.integers(2, 5))
-            teams = [int(rng.integers(1, 64 // n_teams + 1)) for _ in range(n_teams)]
+            teams = [int(rng.integers(1, (128 if rng.random() < 0.2 else 64) // n_teams + 1)) for _ in range(n_teams)]
             side = float(rng.choice([3.0, 6.0, 12.0, 30.0]))
             desc = dict(kind="tdm", teams=teams, side=side)
             try:
@@ -78,7 +78,7 @@ def main():
             tdm_cases += 1
             agent_steps += E * sum(teams) * steps
             continue
-        N = int(rng.choice([2, 3, 4, 5, 6, 7, 8, 9, 12, 16, 17, 24, 31, 32, 33, 40, 45, 48, 63, 64]))
+        N = int(rng.choice([2, 3, 4, 5, 6, 7, 8, 9, 12, 16, 17, 24, 31, 32, 33, 40, 45, 48, 63, 64, 65, 80, 100, 128]))
         E = int(rng.choice([3, 16, 40]))
         # side of the spawn square: from a pile (about one body area per agent) to the reference's 20 m
         spread = float(np.sqrt(N) * rng.choice([0.9, 1.3, 2.0, 3.5]) if rng.random() < 0.7 else 20.0)

@@ -71,7 +71,7 @@ def test_no_cpu_fallback(built):
     p = built.default_params(built.FLOCK)
     h = C.c_void_p()
     assert built.lib().macm_create(C.byref(h), C.byref(p), 0) == -2 and not h
-    p.n_agents = 65
+    p.n_agents = 129      # MACM_MAX_AGENTS is 128
     assert built.lib().macm_create(C.byref(h), C.byref(p), 0) == -1
 
 

@@ -101,3 +101,13 @@ def test_nn_exact_draws_on_a_lattice(N, cols):
         assert np.array_equal(env.state["nn_idx"].cpu().numpy(), o["nn_idx"]), "step %d" % k
         compare_obs(env.state["obs"].cpu().numpy(), o, "polar", k)
     env.close()
+
+
+def test_more_than_64_agents_per_env():
+    """The reference has no cap on n_agents (mvmnt.py:61); envs of 65..128 agents run four agents per lane with
+    128-bit contact adjacency rows.  Same bars as everywhere: engine state, contact lists, ids bit-exact."""
+    run_parity(24, 96, 60, seed=31, reward_mode="linear")                                  # the reference's 20 m spawn square
+    run_parity(12, 128, 50, seed=32, spread=14.0, targets=[i % 3 for i in range(128)])      # full width, three targets, denser
+    st = run_parity(8, 80, 40, seed=33, spread=8.0, max_contacts=80 * 79 // 2, max_touching=240)   # a pile: multi-contact islands
+    assert st["max_touching"] > 32       # the level-scheduled solver path of the wide shape ran
+    run_parity(6, 70, 300, seed=34, policy="flock", check_every=25, max_contacts=70 * 69 // 2, max_touching=240)

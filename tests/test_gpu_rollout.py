@@ -34,6 +34,7 @@ def _flock_pair(E, n_agents, seed, **kw):
     (6, 200, dict(targets=[0, 0, 1, 1, 2, 2])),                 # configs[2]: four envs per warp
     (16, 64, dict(coord="cartesian", start_spread=6.0)),        # crowded, cartesian observations
     (33, 40, dict(start_spread=8.0)),                           # ragged: 33 agents on 64 slots, dense contacts
+    (100, 30, dict(start_spread=12.0)),                         # more than 64 agents: four per lane, 128-bit sets
 ])
 def test_rollout_equals_steps_flock(N, E, kw):
     import torch

@@ -85,3 +85,10 @@ def test_tdm_crowded_many_deaths():
     # a small arena: agents in melee range all the time -> health, deaths, winners, contact destruction
     d = run_tdm(48, [6, 6, 6], 700, seed=3, width=6.0, height=6.0, attack_p=0.9, check_every=20)
     assert d > 48
+
+
+def test_tdm_more_than_64_agents():
+    # three teams of 30: 90 agents per arena, four agents per lane
+    d = run_tdm(12, [30, 30, 30], 200, seed=5, check_every=10)
+    d2 = run_tdm(8, [40, 35], 300, seed=6, width=12.0, height=12.0, attack_p=0.9, check_every=25)
+    assert d + d2 > 0
