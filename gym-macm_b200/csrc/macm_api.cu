@@ -187,6 +187,8 @@ static int derive_constants(macm_sim* sim)
     if (C < 1) C = 1;
     int TC = p.max_touching > 0 ? p.max_touching : (C < 2 * p.n_agents ? C : 2 * p.n_agents);
     if (TC > C) TC = C;
+    // envs of 65..128 agents: the default leaves room for one 448-thread block (14 envs) per SM in shared memory
+    if (p.max_touching <= 0 && p.n_agents > 64 && TC > 192) TC = 192;
     TC = (TC + 15) / 16 * 16;
     // macm_rollout parks 20 bytes per agent slot in the (24-byte-per-entry) touching-contact stage between steps
     {

@@ -82,7 +82,7 @@ typedef struct macm_params {
     int32_t n_agents;             /* sum(n_agents) of the ctor (mvmnt.py:61), 2..MACM_MAX_AGENTS */
     int32_t n_targets;            /* len(unique(targets)) (mvmnt.py:42), 1..MACM_MAX_TARGETS; TDM: 0 */
     int32_t max_contacts;         /* contact capacity per env; 0 = min(N(N-1)/2, 8N) */
-    int32_t max_touching;         /* touching-contact capacity per env (solver staging); 0 = min(max_contacts, 2N) */
+    int32_t max_touching;         /* touching-contact capacity per env (solver staging, at most 240); 0 = min(max_contacts, 2N), 192 beyond 64 agents */
     double hz;                    /* settings.py:30   60.0 */
     int32_t velocity_iterations;  /* settings.py:31   8 */
     int32_t position_iterations;  /* settings.py:32   3 */
