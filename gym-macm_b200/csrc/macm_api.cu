@@ -483,6 +483,7 @@ extern "C" int macm_rollout(macm_sim* sim, const void* actions, int32_t n_steps,
     R.K = n_steps;
     R.policy = -1;
     R.seed = seed;
+    R.sc = sample_const(sim, sim->auto_seed);
     R.sync = sim->cfg.threads > 128 ? 1 : 0;   // wide blocks: the warps of a block run each step in step
     if (const char* e = getenv("MACM_ROLLOUT_SYNC")) R.sync = atoi(e);   // experiments
     if (actions) {

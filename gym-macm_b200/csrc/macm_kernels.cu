@@ -1934,6 +1934,41 @@ __global__ void __launch_bounds__(shape_max_threads(G, APL), 1) macm_step_kernel
     }
 
     PHASE_STAMP(11);
+    // ---- auto-reset inside a rollout (MACM_FLAG_AUTO_RESET): an env that is done starts its next episode before the
+    // step's observation is written -- the draws, the body creation and the order of events of macm_reset_masked
+    // (the launch the flag appends to a single step), so K steps in one launch stay bit-identical to K single
+    // steps.  The launch's last step leaves the reset to that appended launch: its state is already written back.
+    if (ROLL && !last && (P.flags & MACM_FLAG_AUTO_RESET) && done) {
+        const uint32_t episode = ((uint32_t)eflags >> MACM_ENV_EPISODE_SHIFT) + 1u;
+        g.sync();
+#pragma unroll
+        for (int s = 0; s < APL; ++s) {
+            const int i = g.gl + s * G;
+            if (valid[s]) {
+                float x, y, a;
+                sample_agent(P, R_.sc, (uint64_t)env * N + i + (uint64_t)P.env_base * N, i, episode, x, y, a);
+                const float r = P.radius;
+                c[s] = make_float2(x, y); v[s] = make_float2(0.0f, 0.0f); ang[s] = a; slp[s] = 0.0f;
+                fatr[s] = make_float4((x - r) - B2_AABB_EXTENSION, (y - r) - B2_AABB_EXTENSION,
+                                      (x + r) + B2_AABB_EXTENSION, (y + r) + B2_AABB_EXTENSION);
+                pos[i] = c[s];
+                if (TDM) { health[s] = P.init_health; cd_atk[s] = 0; cd_mov[s] = 0; hits[s] = 0; S.ang()[i] = a; }
+                else S.tgt()[i] = sample_target(R_.sc, (uint64_t)(env + P.env_base) * P.T + (P.T == 1 ? 0 : (int)P.target_idx[i]), episode);
+            }
+            if (TDM) now_alive[s] = valid[s];
+        }
+        if (!TDM)
+            for (int t = g.gl; t < P.T; t += G)
+                const_cast<float2*>(P.targets)[(size_t)env * P.T + t] = sample_target(R_.sc, (uint64_t)(env + P.env_base) * P.T + t, episode);
+        if (TDM) {
+            alive = empty_set<ASet>();
+#pragma unroll
+            for (int s = 0; s < APL; ++s) { put_slot<G>(alive, s, g.ballot(valid[s])); was_alive[s] = valid[s]; }
+        }
+        cnt = 0; step_cnt = 0; winner = -1;
+        eflags = MACM_ENV_FRESH | (int)(episode << MACM_ENV_EPISODE_SHIFT);
+        g.sync();
+    }
     // ---- phase 13: observations (mvmnt.py:181-222 / combat.py:206-227) ----------------------------
     // Between two steps of a rollout the velocities, fat AABBs and sleep timers wait in shared memory (the
     // velocity array and the touching-contact stage, both idle until the next step's phase 2), so that the
@@ -2012,8 +2047,8 @@ __global__ void __launch_bounds__(128) macm_observe_kernel(const __grid_constant
             P.angsleep[gi] = make_float2(a, 0.0f);
             P.fat[gi] = make_float4((x - r) - B2_AABB_EXTENSION, (y - r) - B2_AABB_EXTENSION,
                                     (x + r) + B2_AABB_EXTENSION, (y + r) + B2_AABB_EXTENSION);
-            P.rewards[gi] = 0.0f;
-            P.collided[gi] = 0;
+            // (rewards, collided and done keep the values of the env's last step: the learner reads the terminal
+            //  reward next to the new episode's first observation)
             if (KIND == MACM_ENV_TDM)
                 P.tdm[gi] = make_float4(P.init_health, __int_as_float(0), __int_as_float(0), __int_as_float(1));
         }

@@ -57,21 +57,22 @@ struct SimConst {
     int bulk;
 };
 
+// Initial-state distributions (mvmnt.py:48-52,62-64; combat.py:84-86) and the key of the counter-based draws.
+struct SampleConst {
+    unsigned long long seed;
+    double spread, sx, sy, tmin, tmax, width, height;
+};
+
 // Arguments of a multi-step launch (macm_rollout): K consecutive steps of every env inside one kernel, the env's
 // state staying on chip between them.  Per-step outputs go to the caller's [K, ...] arrays (any of them may be
 // null); the sim's bound output buffers receive the last step's values, exactly as after K calls of macm_step.
 struct Rollout {
+    SampleConst sc;     // distributions and seed of the in-launch resets (MACM_FLAG_AUTO_RESET)
     int K;              // steps in this launch (macm_step: 1)
     int sync;           // the block's warps start every `sync`-th step together (0 = never; 1 with one block per SM)
     int policy;         // MACM_BOT_* when `actions` is null (the actions=None mode of mvmnt.py:86-92), else -1
     unsigned long long seed;
     float* obs; int* nn_idx; float* rewards; uint8_t* collided; uint8_t* done;
-};
-
-// Initial-state distributions (mvmnt.py:48-52,62-64; combat.py:84-86) and the key of the counter-based draws.
-struct SampleConst {
-    unsigned long long seed;
-    double spread, sx, sy, tmin, tmax, width, height;
 };
 
 struct LaunchCfg {

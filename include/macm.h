@@ -57,7 +57,9 @@ enum { MACM_DAMPING_TAYLOR = 0, MACM_DAMPING_PADE = 1 };
 enum {
     MACM_FLAG_REPAIR_MOV_COOLDOWN = 1, /* cooldown_mov_penalty counts down */
     MACM_FLAG_AUTO_RESET = 2           /* every macm_step / macm_rollout launch is followed by macm_reset_masked(NULL):
-                                          envs whose `done` flag is set start a new episode (see macm_reset_masked) */
+                                          envs whose `done` flag is set start a new episode (see macm_reset_masked);
+                                          inside a macm_rollout launch the same reset happens after every step, so the
+                                          per-step outputs are those of n_steps single steps with the flag set */
 };
 /* env_state[e][1]: bits 0-2 flags, bits 8-31 the env's episode counter (incremented by macm_reset_masked) */
 enum {
@@ -201,8 +203,9 @@ int macm_sample_reset(macm_sim* sim, uint64_t seed, void* stream);
  * macm_sample_reset keyed by (seed, global env, agent, episode), episode = the env's reset count, so two
  * episodes of one env differ and a batch is the same however it is sharded), then what macm_reset does for it:
  * fat AABBs, no contacts, step_count 0, MACM_ENV_FRESH, cleared overflow bits, TDM health / cool-downs /
- * alive, rewards and collided 0, the first observation of the new episode in `obs` / `nn_idx`.  `done` is
- * left as it is (the learner reads it; the next step overwrites it).  One launch, no host synchronisation. */
+ * alive, the first observation of the new episode in `obs` / `nn_idx`.  `rewards`, `collided` and `done` keep the
+ * values of the env's last step (the learner reads the terminal reward next to the new episode's first observation;
+ * the next step overwrites them).  One launch, no host synchronisation. */
 int macm_reset_masked(macm_sim* sim, const uint8_t* mask, uint64_t seed, void* stream);
 /* Seed of the resets that MACM_FLAG_AUTO_RESET appends to every step (default 0). */
 int macm_set_auto_reset_seed(macm_sim* sim, uint64_t seed);

@@ -140,3 +140,46 @@ def test_tdm_envs_end_at_different_steps_and_reset_alone():
             n_resets += len(new)
     assert n_resets >= 8 and len(set(ended_at[ended_at >= 0])) >= 3      # matches ended at different steps
     assert int(env.episode.max()) >= 1
+
+
+def test_auto_reset_inside_a_rollout_equals_single_steps():
+    """With auto_reset a K-step macm_rollout restarts finished envs between its steps exactly as K single steps with
+    the flag do (same draws, same order of events): per-step outputs and final state bit-identical."""
+    import torch
+    import gym_macm
+    from test_gpu_rollout import _same_state
+    # Flock: every env hits the time limit on step 13 (mvmnt.py:134-136), three times in 40 steps
+    E, N, K = 48, 64, 40
+    one, many = [gym_macm.BatchedFlock(E, n_agents=[N], device="cuda:0", seed=8, time_limit=0.2, auto_reset=True,
+                                       start_spread=10.0, targets=[i % 2 for i in range(N)]) for _ in range(2)]
+    for e in (one, many):
+        e.engine.set_auto_reset_seed(77)
+    acts = torch.zeros((K, E, N, 4), dtype=torch.uint8, device="cuda:0")
+    acts[..., :3] = torch.randint(0, 3, (K, E, N, 3), device="cuda:0", dtype=torch.uint8)
+    per = {n: [] for n in ("obs", "nn_idx", "rewards", "collided", "done")}
+    for k in range(K):
+        one.step(acts[k])
+        for n in per:
+            per[n].append(one.state[n].clone())
+    out = many.rollout(acts)
+    torch.cuda.synchronize()
+    for n in per:
+        assert torch.equal(out[n], torch.stack(per[n])), n
+    _same_state(one, many, "flock auto-reset")
+    assert torch.equal(one.state["targets"], many.state["targets"])
+    assert int(one.episode.min()) == 3 and int(out["done"].sum()) == 3 * E
+    # TDM with the combat actor: matches end at different steps (combat.py:171-182)
+    E, K = 40, 400
+    one, many = [gym_macm.BatchedTDM(E, n_agents=[3, 3], device="cuda:0", seed=9, world_width=5.0, world_height=4.0,
+                                     auto_reset=True) for _ in range(2)]
+    rew, done = [], []
+    for k in range(K):
+        one.step(one.bot_actions("combat"))
+        rew.append(one.state["rewards"].clone())
+        done.append(one.state["done"].clone())
+    out = many.rollout(None, n_steps=K, policy="combat", want=("rewards", "done"))
+    assert torch.equal(out["rewards"], torch.stack(rew)) and torch.equal(out["done"], torch.stack(done))
+    _same_state(one, many, "tdm auto-reset")
+    d = torch.stack(done).cpu().numpy()                      # [K, E]
+    first = np.where(d.any(0), d.argmax(0), -1)
+    assert int(one.episode.max()) >= 1 and len(set(first[first >= 0].tolist())) >= 3      # matches ended at different steps
