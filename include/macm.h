@@ -175,7 +175,10 @@ int macm_params_default(macm_params* p, int env_kind);
 /* Replaces world construction: NoRender(settings) -> FrameworkBase.__init__ ->
  * b2World(gravity=(0,0), doSleep=True) (cm_framework.py:155-167) for n_envs worlds at once.
  * Validates the parameters, derives the fp32 engine constants, selects device `device`.
- * No device memory is allocated here except the pinned staging of the *_host calls (lazily). */
+ * No device memory is allocated here except two small tables and, lazily, the staging of the *_host calls.
+ * On MACM_E_CUDA after the device was found, *out still receives a handle whose only use is
+ * macm_last_cuda_error(*out) followed by macm_destroy(*out) (which frees whatever was allocated); on every other
+ * failure *out is NULL. */
 int macm_create(macm_sim** out, const macm_params* p, int device);
 int macm_destroy(macm_sim* sim);
 
