@@ -529,36 +529,45 @@ def main():
     # done inside the timed region, and the host reads a result before it issues the batch's next step.
     DEPTH = max(1, min(args.e2e_depth, ROT))
     pp = sims[:DEPTH] if args.e2e_steps > 0 else []
-    # what Flock.step returns (mvmnt.py:140,204-220): the observation nodes -- distances / angles AND the nearest
-    # agent's id -- and the rewards, plus env.done; the four arrays are contiguous in the output slab: one transfer
-    want = ("obs", "rewards", "done", "nn_idx")
+    # Two result sets, both contiguous in the output slab (ONE device->host transfer each):
+    #   e2e      obs floats + rewards + done: what a learner consumes (the definition of round 1's line)
+    #   e2e_all  + nearest-agent ids + collided flags: everything the drop-in Flock.step marshals into its dicts
+    #            (mvmnt.py:140,163-178,204-220)
     pin = pp[0].engine.pinned() if pp else {}
     host_actions = [acts[i].cpu().pin_memory() for i in range(4)]
-    for s_ in pp:
-        for k in range(3):
-            s_.engine.step_host(host_actions[k % 4], want=want)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    checksum = 0.0
-    te = time.perf_counter()
-    for k in range(args.e2e_steps):
-        cur = pp[k % DEPTH].engine
-        if k >= DEPTH:
-            cur.host_sync()                                   # results of this batch's previous step
-            checksum += float(cur.pinned()["rewards"][0, 0])  # the host reads them
-        cur.step_host(host_actions[k % 4], want=want, wait=False)
-    for s_ in pp:
-        s_.engine.host_sync()
-    el = time.perf_counter() - te
-    el = T.max_over_ranks(el)
-    h2d = int(host_actions[0].numel() * host_actions[0].element_size())
-    d2h = int(sum(pin[k].numel() * pin[k].element_size() for k in want)) if pp else 0
-    e2e = None if not pp else {"value": world * E * N * args.e2e_steps / el, "unit": UNIT, "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "d2h_transfers_per_step": 1,
-           "pcie_GBps_per_gpu": (h2d + d2h) * args.e2e_steps / el / 1e9,
-           "path": "macm_step_host_async/macm_host_sync on %d batches in rotation: pinned host actions -> device, "
-                   "step kernel, obs (floats + nearest-agent ids) + rewards + done -> pinned host in ONE transfer (output slab)" % DEPTH}
+
+    def e2e_leg(want, steps):
+        for s_ in pp:
+            for k in range(3):
+                s_.engine.step_host(host_actions[k % 4], want=want)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        checksum = 0.0
+        te = time.perf_counter()
+        for k in range(steps):
+            cur = pp[k % DEPTH].engine
+            if k >= DEPTH:
+                cur.host_sync()                                   # results of this batch's previous step
+                checksum += float(cur.pinned()["rewards"][0, 0])  # the host reads them
+            cur.step_host(host_actions[k % 4], want=want, wait=False)
+        for s_ in pp:
+            s_.engine.host_sync()
+        el = T.max_over_ranks(time.perf_counter() - te)
+        h2d = int(host_actions[0].numel() * host_actions[0].element_size())
+        d2h = int(sum(pin[k].numel() * pin[k].element_size() for k in want))
+        return {"value": world * E * N * steps / el, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": steps, "d2h_transfers_per_step": 1,
+                "pcie_GBps_per_gpu": (h2d + d2h) * steps / el / 1e9, "outputs": list(want)}
+
+    e2e = None
+    if pp:
+        e2e = e2e_leg(("obs", "rewards", "done"), args.e2e_steps)
+        e2e["path"] = ("macm_step_host_async/macm_host_sync on %d batches in rotation: pinned host actions -> device, step "
+                       "kernel, obs + rewards + done -> pinned host in ONE transfer (output slab)" % DEPTH)
+        if plain:
+            legs["e2e_all"] = e2e_leg(("obs", "rewards", "done", "nn_idx", "collided"), max(60, args.e2e_steps // 2))
+            legs["e2e_all"]["note"] = "every output of the drop-in Flock.step (obs floats, nearest-agent ids, rewards, collided, done)"
 
     if rank == 0:
         cpu = None
