@@ -4,10 +4,10 @@
 // environment of the batch, i.e. action decode + b2World::Step + reward pass + observation pass.
 //
 // Mapping.  An environment is owned by a GROUP of G lanes of one warp (G = 4, 8, 16 or 32); each
-// lane owns APL agents (agent i lives in lane i % G, slot i / G), so N <= G*APL <= 64.  Groups
+// lane owns APL agents (agent i lives in lane i % G, slot i / G), so N <= G*APL <= 128.  Groups
 // never talk to each other, so all synchronisation is __syncwarp / ballot on the group mask and
 // a block is just a bag of independent groups (no __syncthreads anywhere).  The bodies, the fat
-// AABBs, the contact adjacency (one 64-bit row per agent) and the touching contacts of an
+// AABBs, the contact adjacency (one 64- or 128-bit row per agent) and the touching contacts of an
 // environment are staged in shared memory; HBM is touched once per array per step with
 // coalesced float4 / float2 accesses.
 //
