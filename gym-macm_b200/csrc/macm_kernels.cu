@@ -683,6 +683,69 @@ __device__ __forceinline__ void nn_search_64(const Grp<G>& g, const EnvS<2 * G>&
     }
 }
 
+// Nearest other agent for the FOUR agents of a lane (N in 65..128; agents gl, gl + 32, gl + 64, gl + 96).
+// Every candidate is broadcast in ascending index order, so strict '<' between blocks of four and the lowest index
+// inside the winning block IS the reference's tie-break (mvmnt.py:194) -- no re-scan needed; the price is an explicit
+// self test, paid only by the slot whose own 32-block is being visited (the loop is unrolled over the four blocks).
+// Squared distances in packed fp32x2 for the agent pairs (0, 1) and (2, 3): positions are staged as
+// (x, x, y, y), so the two operand pairs of a candidate come out of one 16-byte load.
+template <int G>
+__device__ __forceinline__ void nn_search_128(const Grp<G>& g, const EnvS<4 * G>& S, const float2 (&o)[4], float (&best)[4],
+                                              int (&bi)[4])
+{
+    static_assert(G == 32, "four agents per lane means 32 lanes per env");
+    const float2* pos = S.pos();
+    float4* P4 = reinterpret_cast<float4*>(S.fat());   // the fat AABBs are dead by now
+    g.sync();
+#pragma unroll
+    for (int s = 0; s < 4; ++s) P4[g.gl + 32 * s] = make_float4(o[s].x, o[s].x, o[s].y, o[s].y);
+    g.sync();
+    const float BIG = 3.4028234664e38f;   // every real squared distance is below it; padding agents give +inf
+    const f32x2 ox01 = pack2(o[0].x, o[1].x), oy01 = pack2(o[0].y, o[1].y);
+    const f32x2 ox23 = pack2(o[2].x, o[3].x), oy23 = pack2(o[2].y, o[3].y);
+    float bm[4] = {BIG, BIG, BIG, BIG};   // running minimum per agent
+    int kb[4] = {0, 0, 0, 0};             // first candidate of the block of four it came from
+#pragma unroll
+    for (int blk = 0; blk < 4; ++blk) {   // the 32-block that holds this lane's agent `blk`
+#pragma unroll 1
+        for (int b = 32 * blk; b < 32 * blk + 32; b += 4) {
+            float d[4][4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float4 q = P4[b + k];
+                const f32x2 qx = pack2(q.x, q.y), qy = pack2(q.z, q.w);
+                const f32x2 dx01 = sub2(qx, ox01), dy01 = sub2(qy, oy01), dx23 = sub2(qx, ox23), dy23 = sub2(qy, oy23);
+                float xl, xh, yl, yh;
+                unpack2(mul2(dx01, dx01), xl, xh); unpack2(mul2(dy01, dy01), yl, yh);
+                d[k][0] = __fadd_rn(xl, yl); d[k][1] = __fadd_rn(xh, yh);   // b2DistanceSquared, no FMA
+                unpack2(mul2(dx23, dx23), xl, xh); unpack2(mul2(dy23, dy23), yl, yh);
+                d[k][2] = __fadd_rn(xl, yl); d[k][3] = __fadd_rn(xh, yh);
+                if (b + k - 32 * blk == g.gl) d[k][blk] = BIG;              // an agent is not its own neighbour
+            }
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const float m = fminf(fminf(fminf(d[0][s], d[1][s]), d[2][s]), d[3][s]);
+                const bool p = m < bm[s];
+                bm[s] = fminf(bm[s], m);
+                kb[s] = p ? b : kb[s];
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        best[s] = bm[s];
+        bi[s] = 128;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = kb[s] + k;
+            const float2 q = pos[c];
+            const float ax = q.x - o[s].x, ay = q.y - o[s].y;
+            const float dd = ax * ax + ay * ay;
+            if (c != g.gl + 32 * s && dd == bm[s]) bi[s] = min(bi[s], c);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // observation pass for the agents a lane owns (Flock.get_obs, mvmnt.py:181-222)
 // ------------------------------------------------------------------------------------------
@@ -721,6 +784,8 @@ __device__ void flock_observe(const Grp<G>& g, const EnvS<G * APL>& S, const Sim
     // Slot s only has to skip itself while j runs through its own 32-block.
     if constexpr (APL == 2) {
         nn_search_64<G>(g, S, o[0], o[APL - 1], best[0], bi[0], best[APL - 1], bi[APL - 1]);
+    } else if constexpr (APL == 4) {
+        nn_search_128<G>(g, S, o, best, bi);
     } else {
 #pragma unroll
         for (int jb = 0; jb < G * APL; jb += G) {
