@@ -196,8 +196,9 @@ static int derive_constants(macm_sim* sim)
         const int need = (20 * slots + 23) / 24;
         if (TC < need) TC = (need + 15) / 16 * 16;
     }
-    if (TC > 240) TC = 240;  // levels are bytes; the DFS keeps one taken-bit per chunk of G contacts
-    K.C = C; K.TC = TC;
+    int TCH = 0;             // beyond the shared-memory stage: a global-memory one of the requested capacity
+    if (TC > 240) { TCH = (TC + 7) / 8 * 8; TC = 240; }  // (shared-memory stage: levels and list links are bytes)
+    K.C = C; K.TC = TC; K.TCH = TCH;
     K.kind = p.env_kind; K.reward_mode = p.reward_mode; K.action_mode = p.action_mode; K.coord = p.coord;
     K.vel_iters = p.velocity_iterations; K.pos_iters = p.position_iterations;
     K.warm_starting = p.warm_starting; K.flags = p.flags;
@@ -293,6 +294,7 @@ extern "C" int macm_create(macm_sim** out, const macm_params* p, int device)
     e = macm_launch_cfg(sim->K, sim->sm_count, &sim->cfg);
     if (e != cudaSuccess) { *out = nullptr; delete sim; return MACM_E_INVALID; }
     CU(macm_prepare_kernels(sim->K, sim->cfg, &sim->blocks_per_sm));
+    if (sim->K.TCH > 0) CU(macm_prepare_kernels_huge(sim->K, sim->cfg));
     sim->K.first_wave = sim->sm_count * (sim->blocks_per_sm > 0 ? sim->blocks_per_sm : 1);
     // sin/cos(k/128), k = 0..417, as float64: the table behind the action decode's np.cos/np.sin
     {
@@ -338,9 +340,10 @@ extern "C" int macm_get_buffer_sizes(const macm_sim* sim, macm_buffer_sizes* o)
     o->tdm_state = K.kind == MACM_ENV_TDM ? EN * 16 : 0; o->team = K.kind == MACM_ENV_TDM ? (uint64_t)K.N : 0;
     o->obs = EN * 4 * (uint64_t)K.obs_dim; o->nn_idx = K.kind == MACM_ENV_FLOCK ? EN * 4 : 0;
     o->rewards = EN * 4; o->collided = EN; o->done = (uint64_t)K.E;
+    o->touch_scratch = (uint64_t)K.E * K.TCH * 32;
     o->obs_dim = K.obs_dim;
     o->action_bytes = sim->params.action_mode == MACM_ACTION_DISCRETE ? 4 : 8;
-    o->max_contacts = K.C; o->max_touching = K.TC;
+    o->max_contacts = K.C; o->max_touching = K.TCH > 0 ? K.TCH : K.TC;
     return MACM_OK;
 }
 
@@ -377,6 +380,8 @@ extern "C" int macm_bind(macm_sim* sim, const macm_buffers* b)
     K.env_state = (int4*)b->env_state; K.targets = (const float2*)b->targets; K.target_idx = b->target_idx;
     K.tdm = (float4*)b->tdm_state; K.team = b->team;
     K.obs = b->obs; K.nn_idx = b->nn_idx; K.rewards = b->rewards; K.collided = b->collided; K.done = b->done;
+    if (K.TCH > 0 && (!b->touch_scratch || !aligned(b->touch_scratch, 16))) return b->touch_scratch ? MACM_E_ALIGN : MACM_E_UNBOUND;
+    K.scratch = K.TCH > 0 ? b->touch_scratch : nullptr;
     K.bulk = flock && K.action_mode == MACM_ACTION_DISCRETE && sim->cfg.G == 32 && (K.N & 3) == 0 && K.C >= 32 &&
              28 * K.N + 384 <= 24 * K.TC && aligned(b->angsleep, 16) && aligned(b->contact_ab, 16) &&
              aligned(b->contact_imp, 16) && ((K.C * 4) & 15) == 0;

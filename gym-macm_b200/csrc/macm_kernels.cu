@@ -26,6 +26,14 @@
 
 #include "macm_sim.h"
 
+// macm_kernels_huge.cu compiles this file a second time with MACM_HUGE_TU defined: the same kernels plus the
+// global-memory touching stage (max_touching > 240), exported as macm_launch_step_huge / macm_prepare_kernels_huge.
+#ifdef MACM_HUGE_TU
+#define MACM_HUGE_BUILD 1
+#else
+#define MACM_HUGE_BUILD 0
+#endif
+
 // Launch shapes: 128-thread blocks, 7 per SM (72 registers); or, for one-env-per-warp groups (N > 16),
 // one 896-thread block per SM.  (Measured on B200, profiles/README.md: the
 // warp scheduler favours the warps of the oldest resident block, so with seven small blocks the last
@@ -883,6 +891,199 @@ __device__ void tdm_observe(const Grp<G>& g, const EnvS<G * APL>& S, const SimCo
     }
 }
 
+#if MACM_HUGE_BUILD
+// ------------------------------------------------------------------------------------------
+// Envs with more touching contacts than the shared-memory stage holds (tc > TC <= 240: overlapping spawn piles; bodies
+// that do not overlap cannot touch more than ~3N others).  With a global-memory stage bound (macm_buffers.touch_scratch,
+// max_touching > 240) such an env is solved here, exactly, in Box2D's island order like the dense-pile path above --
+// 16-bit contact indices and levels, every array in global memory, one lane replaying the traversal.  Cold and slow
+// by design; without the stage the env is flagged MACM_ENV_TOUCH_OVERFLOW instead.
+// ------------------------------------------------------------------------------------------
+struct HugeStage {
+    float2* n; float2* imp; uint32_t* ew; uint16_t* na; uint16_t* nb; uint16_t* slot; uint32_t* ord; int cap;
+    __device__ HugeStage(const SimConst& P, int env)
+    {
+        unsigned char* b = P.scratch + (size_t)env * P.TCH * 32;
+        const size_t T = (size_t)P.TCH;
+        n = (float2*)b; imp = (float2*)(b + 8 * T); ew = (uint32_t*)(b + 16 * T); na = (uint16_t*)(b + 20 * T);
+        nb = (uint16_t*)(b + 22 * T); slot = (uint16_t*)(b + 24 * T); ord = (uint32_t*)(b + 28 * T); cap = P.TCH;
+    }
+};
+#define HUGE_NONE 0xffffu
+#define HUGE_TAKEN 0x80000000u
+
+// Stages every touching contact of the env's HBM list (birth order), replays the island traversal, solves the velocity
+// constraints and stores the impulses.  Returns the number of levels (bit 30 set when even the global-memory stage
+// was too small), or 0 when the env fits the shared-memory stage after all (exactly TC touching contacts) and nothing
+// was done.
+template <int G, int APL>
+__device__ __noinline__ int solve_velocity_huge(const Grp<G>& g, const EnvS<G * APL>& S, const SimConst& P, int env, int cnt,
+                                                const uint32_t* c_ab, float2* c_imp, float ratio)
+{
+    bool overflow = false;
+    constexpr int NC = G * APL;
+    const float2* pos = S.pos(); float2* vel = S.vel();
+    uint32_t* label = S.label();
+    const HugeStage H(P, env);
+    // 1. stage: edges, HBM slots, impulses (the first TC were staged in shared memory by phase 2, the rest kept theirs in
+    //    the HBM list), world normals at the pre-integration positions, impulses scaled by dtRatio
+    int ht = 0;
+    for (int base = 0; base < cnt; base += G) {
+        const int k = base + g.gl;
+        const uint32_t ab = k < cnt ? c_ab[k] : 0u;
+        const bool touch = (ab >> 16) & 1u;
+        const unsigned tm = g.ballot(touch);
+        const int t = ht + __popc(tm & g.below());
+        if (touch) {
+            if (t < H.cap) {
+                const int a = ab & 0xff, b = (ab >> 8) & 0xff;
+                H.ew[t] = (uint32_t)a | ((uint32_t)b << 8);
+                H.slot[t] = (uint16_t)k;
+                float2 im = t < P.TC ? S.t_imp()[t] : c_imp[k];
+                const float2 pa = pos[a], pb = pos[b];
+                float nx = 1.0f, ny = 0.0f;
+                const float dx = pb.x - pa.x, dy = pb.y - pa.y;
+                if ((dx * dx + dy * dy) > B2_EPSILON * B2_EPSILON) { nx = dx; ny = dy; b2normalize(nx, ny); }
+                if (P.warm_starting) { im.x = ratio * im.x; im.y = ratio * im.y; } else im = make_float2(0.0f, 0.0f);
+                H.n[t] = make_float2(nx, ny);
+                H.imp[t] = im;
+            } else {
+                overflow = true;
+            }
+        }
+        ht += __popc(tm);
+    }
+    if (ht <= P.TC) return 0;   // (uniform) the shared-memory path takes it
+    const int tc = ht < H.cap ? ht : H.cap;
+    // 2. islands: per-body edge lists (head-inserted in birth order), depth-first from the highest body left, edges
+    //    newest-first; every contact gets its place in the island order and a level
+    uint16_t* head = reinterpret_cast<uint16_t*>(S.nw());
+    uint16_t* lastlvl = head + NC;
+#pragma unroll
+    for (int s = 0; s < APL; ++s) { head[g.gl + s * G] = HUGE_NONE; lastlvl[g.gl + s * G] = 0; }
+    g.sync();
+    int L = 1;
+    if (g.gl == 0) {
+        uint8_t* stack = S.stack();
+        constexpr int W = NC > 64 ? 4 : 2;
+        uint32_t rem[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) rem[w] = 0u;
+        for (int t = 0; t < tc; ++t) {
+            const uint32_t ew = H.ew[t];
+            const int a = ew & 0xff, b = (ew >> 8) & 0xff;
+            H.na[t] = head[a]; H.nb[t] = head[b];
+            head[a] = (uint16_t)t; head[b] = (uint16_t)t;
+            rem[a >> 5] |= 1u << (a & 31);
+            rem[b >> 5] |= 1u << (b & 31);
+        }
+        int nord = 0;
+        for (;;) {
+            int seed = -1;
+#pragma unroll
+            for (int w = W - 1; w >= 0; --w)
+                if (seed < 0 && rem[w]) seed = w * 32 + 31 - __clz((int)rem[w]);
+            if (seed < 0) break;
+            int sp = 0;
+            stack[sp++] = (uint8_t)seed;
+            rem[seed >> 5] &= ~(1u << (seed & 31));
+            while (sp > 0) {
+                const int b = stack[--sp];
+                label[b] = (uint32_t)seed;
+                for (int t = head[b]; t != HUGE_NONE;) {
+                    const uint32_t ew = H.ew[t];
+                    const int ta = ew & 0xff, tb = (ew >> 8) & 0xff;
+                    const int nx = (ta == b) ? H.na[t] : H.nb[t];
+                    if (!(ew & HUGE_TAKEN)) {
+                        H.ew[t] = ew | HUGE_TAKEN;
+                        const int l = 1 + max((int)lastlvl[ta], (int)lastlvl[tb]);
+                        H.ord[nord++] = (uint32_t)t | ((uint32_t)l << 16);
+                        lastlvl[ta] = (uint16_t)l; lastlvl[tb] = (uint16_t)l;
+                        L = max(L, l);
+                        const int other = (ta == b) ? tb : ta;
+                        const uint32_t ob = 1u << (other & 31);
+                        if (rem[other >> 5] & ob) { rem[other >> 5] &= ~ob; stack[sp++] = (uint8_t)other; }
+                    }
+                    t = nx;
+                }
+            }
+        }
+    }
+    L = g.shfl(L, 0);
+    g.sync();
+    // 3. warm start (it == -1) and the velocity iterations, level by level
+    const float mass_n = P.normal_mass, mass_t = P.normal_mass;
+    for (int it = -1; it < P.vel_iters; ++it) {
+        for (int lev = 1; lev <= L; ++lev) {
+            for (int k = g.gl; k < tc; k += G) {
+                const uint32_t ol = H.ord[k];
+                if ((int)(ol >> 16) != lev) continue;
+                const int t = ol & 0xffff;
+                const uint32_t ew = H.ew[t];
+                const int a = ew & 0xff, b = (ew >> 8) & 0xff;
+                const float2 n = H.n[t];
+                float2 im = H.imp[t];
+                float2 va = vel[a], vb = vel[b];
+                if (it < 0) warm_start(n.x, n.y, im.x, im.y, P.inv_mass, va, vb);
+                else solve_velocity(n.x, n.y, P.friction, mass_n, mass_t, P.inv_mass, im.x, im.y, va, vb);
+                vel[a] = va; vel[b] = vb;
+                H.imp[t] = im;
+            }
+            g.sync();
+        }
+    }
+    // StoreImpulses -> manifold (next step's warm start)
+    for (int t = g.gl; t < tc; t += G) c_imp[H.slot[t]] = H.imp[t];
+    if (g.gl == 0) S.misc()[3] = (uint32_t)tc;   // for solve_position_huge
+    g.sync();
+    return L | (g.ballot(overflow) ? (1 << 30) : 0);
+}
+
+template <int G, int APL>
+__device__ __noinline__ void solve_position_huge(const Grp<G>& g, const EnvS<G * APL>& S, const SimConst& P, int env, int L)
+{
+    float2* pos = S.pos();
+    const uint32_t* label = S.label();
+    uint8_t* isl_act = S.isl_act(); uint8_t* isl_bad = S.isl_bad();
+    const HugeStage H(P, env);
+    const int tc = (int)S.misc()[3];   // how many contacts the velocity part staged
+#pragma unroll
+    for (int s = 0; s < APL; ++s) { isl_act[g.gl + s * G] = 1; isl_bad[g.gl + s * G] = 0; }
+    g.sync();
+    for (int it = 0; it < P.pos_iters; ++it) {
+        for (int lev = 1; lev <= L; ++lev) {
+            for (int k = g.gl; k < tc; k += G) {
+                const uint32_t ol = H.ord[k];
+                if ((int)(ol >> 16) != lev) continue;
+                const uint32_t ew = H.ew[ol & 0xffff];
+                const int a = ew & 0xff, b = (ew >> 8) & 0xff;
+                const int isl = label[a];
+                if (!isl_act[isl]) continue;
+                float2 ca = pos[a], cb = pos[b];
+                const float sep = solve_position(P.radius, P.k_sum, P.inv_mass, ca, cb);
+                pos[a] = ca; pos[b] = cb;
+                if (!(b2min(0.0f, sep) >= -3.0f * B2_LINEAR_SLOP)) isl_bad[isl] = 1;
+            }
+            g.sync();
+        }
+        bool any_bad = false;
+#pragma unroll
+        for (int s = 0; s < APL; ++s) {
+            const int i = g.gl + s * G;
+            const uint8_t bad = isl_bad[i];
+            isl_act[i] = bad;
+            isl_bad[i] = 0;
+            any_bad |= bad != 0;
+        }
+        g.sync();
+        if (!g.ballot(any_bad)) break;
+    }
+#pragma unroll
+    for (int s = 0; s < APL; ++s) S.solved()[g.gl + s * G] = (P.pos_iters > 0) && !isl_act[g.gl + s * G];
+    g.sync();
+}
+#endif   // MACM_HUGE_BUILD
+
 // ------------------------------------------------------------------------------------------
 // Generic contact solver for environments with more touching contacts than lanes (tc > G):
 // every ordered contact goes through shared memory, level by level.  Rare (dense piles) and kept
@@ -1047,6 +1248,41 @@ __device__ __noinline__ int islands_big(const Grp<G>& g, const EnvS<G * APL>& S,
     return L;
 }
 
+#if MACM_HUGE_BUILD
+// The dense-pile solver of the kernels built WITH the global-memory stage (translation unit macm_kernels_huge.cu, launched for
+// sims that bound macm_buffers.touch_scratch; the default kernels are compiled without any of this -- their register
+// allocation is not to be disturbed by a path for overlapping spawn piles, and ptxas allocates per translation unit).  A full shared-memory stage may be a truncated one:
+// then solve_velocity_huge takes the env from its contact list and leaves its level count (and the env index) in the
+// env's MISC words for the position solver.  Returns 1 when even the global stage was too small.
+template <int G, int APL>
+__device__ __noinline__ int solve_velocity_dense_h(const Grp<G>& g, const EnvS<G * APL>& S, const SimConst& P, int env, int cnt,
+                                                   int tc, float ratio, const uint32_t* c_ab, float2* c_imp)
+{
+    if (g.gl == 0) S.misc()[0] = 0u;
+    if (tc == P.TC) {
+        const int r = solve_velocity_huge<G, APL>(g, S, P, env, cnt, c_ab, c_imp, ratio);
+        if (r & 0xffff) {
+            if (g.gl == 0) { S.misc()[0] = (uint32_t)(r & 0xffff); S.misc()[1] = (uint32_t)env; }
+            g.sync();
+            return r >> 30;
+        }
+    }
+    g.sync();
+    const int nlev = islands_big<G, APL>(g, S, tc);
+    if (g.gl == 0) S.misc()[2] = (uint32_t)nlev;
+    solve_velocity_big<G, APL>(g, S, P, tc, nlev, ratio, c_imp);
+    return 0;
+}
+template <int G, int APL>
+__device__ __noinline__ void solve_position_dense_h(const Grp<G>& g, const EnvS<G * APL>& S, const SimConst& P, int tc)
+{
+    g.sync();
+    const int Lh = (int)S.misc()[0];   // (uniform over the group)
+    if (Lh) solve_position_huge<G, APL>(g, S, P, (int)S.misc()[1], Lh);
+    else solve_position_big<G, APL>(g, S, P, tc, (int)S.misc()[2]);
+}
+#endif   // MACM_HUGE_BUILD
+
 // b2World::Step prologue of a world with new fixtures: FindNewContacts before Collide.  Runs on
 // the first step after a reset only; out of line.
 template <int G, int APL>
@@ -1173,6 +1409,7 @@ __global__ void __launch_bounds__(shape_max_threads(G, APL), 1) macm_step_kernel
     constexpr int NC = G * APL;
     constexpr int GPW = 32 / G;
     constexpr bool TDM = KIND == MACM_ENV_TDM;
+    constexpr bool HUGE = MACM_HUGE_BUILD;   // this translation unit's kernels carry the global-memory touching stage
     using EWT = EW<NC>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Grp<G> g;
@@ -1618,7 +1855,7 @@ __global__ void __launch_bounds__(shape_max_threads(G, APL), 1) macm_step_kernel
             tc += __popc(tm);
         }
         cnt = w;
-        if (tc > P.TC) { overflow_t = true; tc = P.TC; }
+        if (tc > P.TC) { overflow_t = !HUGE; tc = P.TC; }   // (HUGE: the global-memory stage takes the env)
         multi = g.ballot(dup) != 0u;
     }
 
@@ -1665,8 +1902,12 @@ __global__ void __launch_bounds__(shape_max_threads(G, APL), 1) macm_step_kernel
 
     // ---- phase 5: contact solver, velocity part -------------------------------------------------
     if (big) {
+#if MACM_HUGE_BUILD
+        if (solve_velocity_dense_h<G, APL>(g, S, P, env, cnt, tc, ratio, c_ab, c_imp)) overflow_t = true;
+#else
         nlev = islands_big<G, APL>(g, S, tc);
         solve_velocity_big<G, APL>(g, S, P, tc, nlev, ratio, c_imp);
+#endif
     } else if (tc > 0) {
         const float mass_n = P.normal_mass, mass_t = P.normal_mass;
         uint32_t* t_ew = S.t_ew();
@@ -1829,7 +2070,11 @@ __global__ void __launch_bounds__(shape_max_threads(G, APL), 1) macm_step_kernel
     PHASE_STAMP(6);
     // ---- phase 7: contact solver, position part (each island stops as soon as it is solved) -------
     if (big) {
+#if MACM_HUGE_BUILD
+        solve_position_dense_h<G, APL>(g, S, P, tc);
+#else
         solve_position_big<G, APL>(g, S, P, tc, nlev);
+#endif
 #pragma unroll
         for (int s = 0; s < APL; ++s) c[s] = pos[g.gl + s * G];
     } else if (tc > 0) {
@@ -2185,10 +2430,12 @@ template <int G, int APL, int KIND>
 cudaError_t launch_one(const SimConst& P, const LaunchCfg& cfg, const void* actions, const Rollout& R, cudaStream_t s,
                        bool observe_only)
 {
+#if !MACM_HUGE_BUILD
     if (observe_only) {
         macm_observe_kernel<G, APL, KIND, false><<<cfg.obs_blocks, 128, cfg.obs_smem_bytes, s>>>(P, nullptr, SampleConst{});
         return cudaGetLastError();
     }
+#endif
     // the step kernel is launched with programmatic stream serialization: it may become resident
     // before its predecessor in the stream has finished and waits in griddepcontrol.wait
     cudaLaunchConfig_t lc = {};
@@ -2201,20 +2448,29 @@ cudaError_t launch_one(const SimConst& P, const LaunchCfg& cfg, const void* acti
     at[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = at;
     lc.numAttrs = 1;
+#if MACM_HUGE_BUILD   // (two instantiations per shape: the single step and the general one)
+    if (R.K == 1 && R.policy < 0 && actions && !R.obs && !R.nn_idx && !R.rewards && !R.collided && !R.done)
+        return cudaLaunchKernelEx(&lc, macm_step_kernel<G, APL, KIND, 0>, P, actions, R);
+    return cudaLaunchKernelEx(&lc, macm_step_kernel<G, APL, KIND, 1>, P, actions, R);
+#else
+    if (P.scratch != nullptr) return macm_launch_step_huge(P, cfg, actions, R, s);   // max_touching > 240: macm_kernels_huge.cu
     if (R.K == 1 && R.policy < 0 && actions) {
         if (!R.obs && !R.nn_idx && !R.rewards && !R.collided && !R.done)
             return cudaLaunchKernelEx(&lc, macm_step_kernel<G, APL, KIND, 0>, P, actions, R);
         return cudaLaunchKernelEx(&lc, macm_step_kernel<G, APL, KIND, 2>, P, actions, R);
     }
     return cudaLaunchKernelEx(&lc, macm_step_kernel<G, APL, KIND, 1>, P, actions, R);
+#endif
 }
 
+#if !MACM_HUGE_BUILD
 template <int G, int APL, int KIND>
 cudaError_t reset_masked_one(const SimConst& P, const LaunchCfg& cfg, const uint8_t* mask, const SampleConst& sc, cudaStream_t s)
 {
     macm_observe_kernel<G, APL, KIND, true><<<cfg.obs_blocks, 128, cfg.obs_smem_bytes, s>>>(P, mask, sc);
     return cudaGetLastError();
 }
+#endif
 
 template <int G, int APL, int KIND>
 cudaError_t prepare_one(const LaunchCfg& cfg, int* blocks_per_sm)
@@ -2224,6 +2480,10 @@ cudaError_t prepare_one(const LaunchCfg& cfg, int* blocks_per_sm)
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(macm_step_kernel<G, APL, KIND, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.smem_bytes);
     if (e != cudaSuccess) return e;
+#if MACM_HUGE_BUILD
+    (void)blocks_per_sm;
+    return cudaSuccess;
+#else
     e = cudaFuncSetAttribute(macm_step_kernel<G, APL, KIND, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.smem_bytes);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(macm_observe_kernel<G, APL, KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -2234,10 +2494,12 @@ cudaError_t prepare_one(const LaunchCfg& cfg, int* blocks_per_sm)
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, macm_step_kernel<G, APL, KIND, 0>, cfg.threads,
                                                          cfg.smem_bytes);
+#endif
 }
 
 }  // namespace
 
+#if !MACM_HUGE_BUILD
 // lanes per env / agents per lane for a given N
 static void pick_shape(int N, int* G, int* APL)
 {
@@ -2291,6 +2553,8 @@ cudaError_t macm_launch_cfg(const SimConst& P, int sm_count, LaunchCfg* cfg)
     return cfg->smem_bytes <= 227 * 1024 ? cudaSuccess : cudaErrorInvalidConfiguration;
 }
 
+#endif   // !MACM_HUGE_BUILD
+
 #define DISPATCH_SHAPE(CALL)                                                        \
     switch ((cfg.G * 8 + cfg.APL) * 2 + (P.kind == MACM_ENV_TDM ? 1 : 0)) {         \
         case (4 * 8 + 1) * 2: return CALL(4, 1, MACM_ENV_FLOCK);                    \
@@ -2308,6 +2572,23 @@ cudaError_t macm_launch_cfg(const SimConst& P, int sm_count, LaunchCfg* cfg)
         default: return cudaErrorInvalidConfiguration;                              \
     }
 
+#if MACM_HUGE_BUILD
+// the exports of macm_kernels_huge.cu
+cudaError_t macm_prepare_kernels_huge(const SimConst& P, const LaunchCfg& cfg)
+{
+    int unused = 0;
+#define CALL(G_, A_, K_) prepare_one<G_, A_, K_>(cfg, &unused)
+    DISPATCH_SHAPE(CALL)
+#undef CALL
+}
+
+cudaError_t macm_launch_step_huge(const SimConst& P, const LaunchCfg& cfg, const void* actions, const Rollout& R, cudaStream_t s)
+{
+#define CALL(G_, A_, K_) launch_one<G_, A_, K_>(P, cfg, actions, R, s, false)
+    DISPATCH_SHAPE(CALL)
+#undef CALL
+}
+#else
 cudaError_t macm_prepare_kernels(const SimConst& P, const LaunchCfg& cfg, int* blocks_per_sm)
 {
 #define CALL(G_, A_, K_) prepare_one<G_, A_, K_>(cfg, blocks_per_sm)
@@ -2344,3 +2625,4 @@ cudaError_t macm_launch_reset(const SimConst& P, cudaStream_t s)
     macm_reset_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(P);
     return cudaGetLastError();
 }
+#endif   // MACM_HUGE_BUILD

@@ -49,6 +49,8 @@ struct SimConst {
     // outputs
     float* obs; int* nn_idx; float* rewards; uint8_t* collided; uint8_t* done;
     unsigned long long* trace;  // [E,4] per-env timing record (macm_set_trace), or null
+    unsigned char* scratch;     // [E, TCH, 32] global-memory solver stage for envs with more than TC touching contacts, or null
+    int TCH;                    // its capacity per env (touching contacts)
     // blocks of the step kernel that are resident at once (SMs x blocks per SM): only those can overlap their L2
     // prefetch with the predecessor's tail; a block of a later wave starts when its loads can be issued anyway
     int first_wave;
@@ -139,6 +141,9 @@ cudaError_t macm_launch_cfg(const SimConst& P, int sm_count, LaunchCfg* cfg);
 cudaError_t macm_prepare_kernels(const SimConst& P, const LaunchCfg& cfg, int* blocks_per_sm);
 cudaError_t macm_launch_step(const SimConst& P, const LaunchCfg& cfg, const void* actions, const Rollout& R, cudaStream_t s);
 cudaError_t macm_launch_observe(const SimConst& P, const LaunchCfg& cfg, cudaStream_t s);
+// implemented in macm_kernels_huge.cu (the kernels with the global-memory touching stage, SimConst::scratch != null)
+cudaError_t macm_prepare_kernels_huge(const SimConst& P, const LaunchCfg& cfg);
+cudaError_t macm_launch_step_huge(const SimConst& P, const LaunchCfg& cfg, const void* actions, const Rollout& R, cudaStream_t s);
 cudaError_t macm_launch_reset(const SimConst& P, cudaStream_t s);
 cudaError_t macm_launch_reset_masked(const SimConst& P, const LaunchCfg& cfg, const uint8_t* mask, const SampleConst& sc,
                                      cudaStream_t s);

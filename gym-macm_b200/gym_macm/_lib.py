@@ -16,7 +16,7 @@ ENV_FRESH, ENV_CONTACT_OVERFLOW, ENV_TOUCH_OVERFLOW = 1, 2, 4
 BOTS = {"idle": 0, "forward": 1, "rotate": 2, "diag": 3, "flock": 4, "random": 5, "combat": 6, "circle": 7}
 FLAG_REPAIR_MOV_COOLDOWN, FLAG_AUTO_RESET = 1, 2
 ENV_EPISODE_SHIFT = 8
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 i32, f64, u64 = C.c_int32, C.c_double, C.c_uint64
 
@@ -40,7 +40,7 @@ class MacmParams(C.Structure):
 
 
 BUFFER_NAMES = ("posvel", "angsleep", "fat", "contact_ab", "contact_imp", "contact_count", "env_state", "targets",
-                "target_idx", "tdm_state", "team", "obs", "nn_idx", "rewards", "collided", "done")
+                "target_idx", "tdm_state", "team", "obs", "nn_idx", "rewards", "collided", "done", "touch_scratch")
 
 
 class MacmBuffers(C.Structure):

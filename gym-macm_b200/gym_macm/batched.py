@@ -89,7 +89,7 @@ class Engine(object):
     _DTYPES = dict(posvel="float32", angsleep="float32", fat="float32", contact_ab="int32", contact_imp="float32",
                    contact_count="int32", env_state="int32", targets="float32", target_idx="uint8",
                    tdm_state="float32", team="uint8", obs="float32", nn_idx="int32", rewards="float32",
-                   collided="uint8", done="uint8")
+                   collided="uint8", done="uint8", touch_scratch="uint8")
 
     def __init__(self, params, device=None):
         torch = _torch()
@@ -123,7 +123,8 @@ class Engine(object):
         Cc, D = self.sizes.max_contacts, self.sizes.obs_dim
         shapes = dict(posvel=(E, N, 4), angsleep=(E, N, 2), fat=(E, N, 4), contact_ab=(E, Cc), contact_imp=(E, Cc, 2),
                       contact_count=(E,), env_state=(E, 4), targets=(E, T, 2), target_idx=(N,), tdm_state=(E, N, 4),
-                      team=(N,), obs=(E, N, D), nn_idx=(E, N), rewards=(E, N), collided=(E, N), done=(E,))
+                      team=(N,), obs=(E, N, D), nn_idx=(E, N), rewards=(E, N), collided=(E, N), done=(E,),
+                      touch_scratch=(int(self.sizes.touch_scratch),))
         self.t = {}
         bufs = _lib.MacmBuffers()
         # The per-step outputs live back to back in ONE device slab (each array 16-byte aligned), in the order

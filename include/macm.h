@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MACM_ABI_VERSION 3
+#define MACM_ABI_VERSION 4
 #define MACM_MAX_AGENTS 128  /* per environment (the reference has no cap, mvmnt.py:61); up to 64: two agents per lane,
                                 beyond: four, with 128-bit contact adjacency rows */
 #define MACM_MAX_TARGETS 16
@@ -84,7 +84,10 @@ typedef struct macm_params {
     int32_t n_agents;             /* sum(n_agents) of the ctor (mvmnt.py:61), 2..MACM_MAX_AGENTS */
     int32_t n_targets;            /* len(unique(targets)) (mvmnt.py:42), 1..MACM_MAX_TARGETS; TDM: 0 */
     int32_t max_contacts;         /* contact capacity per env; 0 = min(N(N-1)/2, 8N) */
-    int32_t max_touching;         /* touching-contact capacity per env (solver staging, at most 240); 0 = min(max_contacts, 2N), 192 beyond 64 agents */
+    int32_t max_touching;         /* touching-contact capacity per env; 0 = min(max_contacts, 2N), 192 beyond 64 agents.  Up to 240 the
+                                     solver's stage lives in shared memory; a larger value adds a global-memory stage
+                                     (macm_buffers.touch_scratch, 32 bytes per contact and env) that takes the rare env
+                                     with more touching contacts than that -- exact, slow, for dense spawn piles */
     double hz;                    /* settings.py:30   60.0 */
     int32_t velocity_iterations;  /* settings.py:31   8 */
     int32_t position_iterations;  /* settings.py:32   3 */
@@ -142,12 +145,14 @@ typedef struct macm_buffers {
     float* rewards;           /* [E,N] */
     uint8_t* collided;        /* [E,N] agent appears in some world contact (mvmnt.py:162-164) */
     uint8_t* done;            /* [E] */
+    /* ---- scratch (only when max_touching > 240 was asked for; see macm_buffer_sizes.touch_scratch) ---- */
+    uint8_t* touch_scratch;   /* the solver's stage of an env with more touching contacts than shared memory holds  16-byte aligned */
 } macm_buffers;
 
 /* Bytes each macm_buffers member must hold for this sim (0 = not used by this env kind). */
 typedef struct macm_buffer_sizes {
     uint64_t posvel, angsleep, fat, contact_ab, contact_imp, contact_count, env_state, targets,
-             target_idx, tdm_state, team, obs, nn_idx, rewards, collided, done;
+             target_idx, tdm_state, team, obs, nn_idx, rewards, collided, done, touch_scratch;
     int32_t obs_dim;          /* floats per agent in `obs` */
     int32_t action_bytes;     /* bytes per agent in the `actions` argument of macm_step */
     int32_t max_contacts, max_touching;

@@ -100,7 +100,7 @@ def main():
         desc = dict(N=N, E=E, spread=round(spread, 2), steps=steps, policy=policy, targets=targets, **kw)
         try:
             st = run_parity(E, N, steps, targets=targets, seed=int(rng.integers(0, 1 << 30)), spread=spread, policy=policy,
-                            max_contacts=N * (N - 1) // 2, max_touching=240, **kw)
+                            max_contacts=N * (N - 1) // 2, max_touching=N * (N - 1) // 2, **kw)
             if cases % 4 == 0:
                 rollout_case(rng, N, E, {k: v for k, v in kw.items()})
         except AssertionError as ex:

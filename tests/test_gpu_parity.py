@@ -111,3 +111,30 @@ def test_more_than_64_agents_per_env():
     st = run_parity(8, 80, 40, seed=33, spread=8.0, max_contacts=80 * 79 // 2, max_touching=240)   # a pile: multi-contact islands
     assert st["max_touching"] > 32       # the level-scheduled solver path of the wide shape ran
     run_parity(6, 70, 300, seed=34, policy="flock", check_every=25, max_contacts=70 * 69 // 2, max_touching=240)
+
+
+def test_piles_beyond_the_shared_memory_stage():
+    """More than 240 touching contacts in one env (an overlapping spawn pile): with max_touching > 240 the global-memory
+    solver stage takes such envs, bit-exact like everything else; without it they are flagged, not silently wrong."""
+    import torch
+    import gym_macm
+    from _parity import make_pair, compare_step
+    for N, spread, seed in ((64, 3.6, 41), (128, 5.5, 42), (33, 2.2, 43)):
+        E = 6
+        env, ref, rng = make_pair(E, N, seed=seed, spread=spread, max_contacts=N * (N - 1) // 2, max_touching=N * (N - 1) // 2)
+        worst = 0
+        for k in range(25):
+            act = rng.integers(0, 3, (E, N, 3))
+            env.step(torch.as_tensor(act, device="cuda:0"))
+            o = ref.flock_step(act)
+            worst = max(worst, max(ref.env_info(e)["touching"] for e in range(E)))
+            compare_step(env, ref, o, k)
+        assert worst > 240, worst          # the global-memory stage was exercised
+        assert env.overflow_count() == (0, 0)
+        env.close()
+    # the same pile on a sim without the stage: reported
+    pos = np.random.default_rng(41).uniform(-1.8, 1.8, (2, 64, 2))
+    flagged = gym_macm.BatchedFlock(2, n_agents=[64], device="cuda:0", seed=None, max_contacts=2016, max_touching=240)
+    flagged.load_state(pos, np.zeros((2, 64)))
+    flagged.step(torch.ones((2, 64, 4), dtype=torch.uint8, device="cuda:0"))
+    assert bool(flagged.overflowed.all())

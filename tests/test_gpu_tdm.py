@@ -26,7 +26,7 @@ def run_tdm(E, teams, steps, seed, width=30.0, height=30.0, attack_p=0.5, check_
     pos = np.stack([rng.random((E, N)) * (team[None] + width / 2), rng.random((E, N)) * height], -1)
     ang = rng.uniform(-1, 1, (E, N)) * np.pi
     env = gym_macm.BatchedTDM(E, n_agents=list(teams), device="cuda:0", seed=None, max_contacts=N * (N - 1) // 2,
-                              max_touching=min(240, 4 * N))
+                              max_touching=N * (N - 1) // 2)
     env.load_state(pos, ang)
     ref = oracle.OracleBatch(E, env_kind=oracle.TDM, n_agents=N, n_targets=0)
     ref.reset(pos, ang, team=team)
