@@ -287,9 +287,10 @@ class _BatchedCommon(object):
 
     @property
     def overflowed(self):
-        """bool [E]: the env ran out of contact capacity (`max_contacts`: newest pairs dropped; `max_touching`, at
-        most 240: the solver skipped the excess) at some step since its last reset -- from that step on its
-        results differ from the reference's.  Sticky until the env is reset."""
+        """bool [E]: the env ran out of contact capacity (`max_contacts`: newest pairs dropped; `max_touching`: the
+        solver skipped the excess) at some step since its last reset -- from that step on its results differ from the
+        reference's.  Sticky until the env is reset.  `max_touching` up to 240 is a shared-memory stage; a larger value
+        (up to `max_contacts`) adds a global-memory stage that takes the rare denser env exactly (spawn piles)."""
         return (self.engine.t["env_state"][:, 1] & (_lib.ENV_CONTACT_OVERFLOW | _lib.ENV_TOUCH_OVERFLOW)) != 0
 
     def overflow_count(self):
