@@ -93,7 +93,7 @@ class TDM(_Base):
         n_agents = _as_list(n_agents)
         nn = sum(n_agents)
         kwargs.setdefault("max_contacts", max(1, nn * (nn - 1) // 2))   # one world: full capacity (see mvmnt.Flock)
-        kwargs.setdefault("max_touching", 240)
+        kwargs.setdefault("max_touching", max(1, nn * (nn - 1) // 2))   # beyond 240: the global-memory solver stage
         self._batch = BatchedTDM(1, n_agents=n_agents, device=device, seed=None, **kwargs)
         self.settings = self._batch.settings
         self.done = False

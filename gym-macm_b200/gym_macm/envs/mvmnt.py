@@ -58,7 +58,7 @@ class Agent(object):
 
 def check_capacity(batch):
     """The dict API never returns results that silently differ from the reference's: a world that ran out of
-    contact capacity (more than 240 touching contacts at once) raises."""
+    contact capacity raises (cannot happen with the capacities the dict API asks for: every pair)."""
     from gym_macm._lib import ENV_CONTACT_OVERFLOW, ENV_TOUCH_OVERFLOW, MacmError
     if int(batch.state["env_state"][0, 1]) & (ENV_CONTACT_OVERFLOW | ENV_TOUCH_OVERFLOW):
         raise MacmError("the world holds more contacts than the simulator's capacity (max_contacts=%d, max_touching=%d)"
@@ -110,11 +110,11 @@ class Flock(_Base):
 
     def __init__(self, n_agents=[10], actors=None, colors=None, targets=None, device=None, **kwargs):
         n_agents = _as_list(n_agents)
-        # one world: room for every possible pair and the largest solver stage, so that a pile at the target
-        # cannot run out of contact capacity (a batch trades that for shared memory, see BatchedFlock.overflowed)
+        # one world: room for every possible pair in the contact list and in the solver's stage, so that no pile
+        # can run out of contact capacity (a batch trades that for shared memory, see BatchedFlock.overflowed)
         nn = sum(n_agents)
         kwargs.setdefault("max_contacts", max(1, nn * (nn - 1) // 2))
-        kwargs.setdefault("max_touching", 240)
+        kwargs.setdefault("max_touching", max(1, nn * (nn - 1) // 2))   # beyond 240: the global-memory solver stage
         self._batch = BatchedFlock(1, n_agents=n_agents, actors=actors, colors=colors, targets=targets,
                                    device=device, seed=None, **kwargs)
         self.settings = self._batch.settings
